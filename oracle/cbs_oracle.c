@@ -1,0 +1,768 @@
+/*
+ * cbs_oracle.c — CPU ORACLE (test infrastructure, NOT product code).
+ * See cbs_oracle.h for scope, conventions and how parity is pinned.
+ *
+ * Every function cites the reference file:line it restates.  Paths are
+ * relative to /root/reference/submission/.
+ */
+#define _GNU_SOURCE
+#include "cbs_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* FFT: tfhe fft64 wrapper semantics (call sites cbs_lib/src/fourier_glwe_keyswitch.rs:301,331,
+ * cbs_lib/src/fourier_glev_ciphertext.rs:155).  N reals are folded to N/2 complex
+ * (a_j + i a_{j+N/2}), twisted by exp(i pi j / N), then a size-N/2 complex DFT with forward
+ * sign -.  Output order is implementation-defined (here: bit-reversed, DIF); all products are
+ * pointwise so only self-consistency matters. */
+typedef struct {
+    int n;           /* complex size = N/2 */
+    double *twr, *twi; /* twist  exp(i*pi*j/N), j<n */
+    double *wr, *wi;   /* exp(-2*pi*i*j/n),     j<n/2 */
+} plan_t;
+
+static plan_t g_plan1024, g_plan256;
+
+static void plan_init(plan_t *p, int N)
+{
+    int n = N / 2;
+    p->n = n;
+    p->twr = malloc(sizeof(double) * n);
+    p->twi = malloc(sizeof(double) * n);
+    p->wr = malloc(sizeof(double) * (n / 2));
+    p->wi = malloc(sizeof(double) * (n / 2));
+    for (int j = 0; j < n; j++) {
+        long double a = M_PIl * (long double)j / (long double)N;
+        p->twr[j] = (double)cosl(a);
+        p->twi[j] = (double)sinl(a);
+    }
+    for (int j = 0; j < n / 2; j++) {
+        long double a = -2.0L * M_PIl * (long double)j / (long double)n;
+        p->wr[j] = (double)cosl(a);
+        p->wi[j] = (double)sinl(a);
+    }
+}
+
+static const plan_t *plan_for(int N)
+{
+    if (N == 1024) return &g_plan1024;
+    if (N == 256) return &g_plan256;
+    fprintf(stderr, "oracle: unsupported polynomial size %d\n", N);
+    abort();
+}
+
+__attribute__((constructor)) static void plans_ctor(void)
+{
+    plan_init(&g_plan1024, 1024);
+    plan_init(&g_plan256, 256);
+}
+
+/* in-place DIF, natural in -> bit-reversed out */
+static void dft_fwd(const plan_t *p, double *re, double *im)
+{
+    int n = p->n;
+    for (int len = n; len >= 2; len >>= 1) {
+        int half = len >> 1, step = n / len;
+        for (int i = 0; i < n; i += len) {
+            for (int j = 0; j < half; j++) {
+                double ur = re[i + j], ui = im[i + j];
+                double vr = re[i + j + half], vi = im[i + j + half];
+                re[i + j] = ur + vr;
+                im[i + j] = ui + vi;
+                double dr = ur - vr, di = ui - vi;
+                double wr = p->wr[j * step], wi = p->wi[j * step];
+                re[i + j + half] = dr * wr - di * wi;
+                im[i + j + half] = dr * wi + di * wr;
+            }
+        }
+    }
+}
+
+/* in-place DIT inverse (unnormalised), bit-reversed in -> natural out */
+static void dft_bwd(const plan_t *p, double *re, double *im)
+{
+    int n = p->n;
+    for (int len = 2; len <= n; len <<= 1) {
+        int half = len >> 1, step = n / len;
+        for (int i = 0; i < n; i += len) {
+            for (int j = 0; j < half; j++) {
+                double wr = p->wr[j * step], wi = -p->wi[j * step];
+                double xr = re[i + j + half], xi = im[i + j + half];
+                double vr = xr * wr - xi * wi, vi = xr * wi + xi * wr;
+                double ur = re[i + j], ui = im[i + j];
+                re[i + j] = ur + vr;
+                im[i + j] = ui + vi;
+                re[i + j + half] = ur - vr;
+                im[i + j + half] = ui - vi;
+            }
+        }
+    }
+}
+
+/* forward_as_integer: signed integers, no scaling */
+void orc_fft_fwd_int(double *out_c, const int64_t *poly, int N)
+{
+    const plan_t *p = plan_for(N);
+    int n = p->n;
+    double re[512], im[512];
+    for (int j = 0; j < n; j++) {
+        double a = (double)poly[j], b = (double)poly[j + n];
+        re[j] = a * p->twr[j] - b * p->twi[j];
+        im[j] = a * p->twi[j] + b * p->twr[j];
+    }
+    dft_fwd(p, re, im);
+    for (int j = 0; j < n; j++) {
+        out_c[2 * j] = re[j];
+        out_c[2 * j + 1] = im[j];
+    }
+}
+
+/* forward_as_torus: u64 read as i64, scaled by 2^-64 */
+void orc_fft_fwd_torus(double *out_c, const uint64_t *poly, int N)
+{
+    const plan_t *p = plan_for(N);
+    int n = p->n;
+    double re[512], im[512];
+    const double s = 0x1p-64;
+    for (int j = 0; j < n; j++) {
+        double a = (double)(int64_t)poly[j] * s, b = (double)(int64_t)poly[j + n] * s;
+        re[j] = a * p->twr[j] - b * p->twi[j];
+        im[j] = a * p->twi[j] + b * p->twr[j];
+    }
+    dft_fwd(p, re, im);
+    for (int j = 0; j < n; j++) {
+        out_c[2 * j] = re[j];
+        out_c[2 * j + 1] = im[j];
+    }
+}
+
+static inline uint64_t torus_from_double(double x)
+{
+    /* tfhe UnsignedTorus::from_torus: fractional part, times 2^64, round, wrap */
+    double f = x - nearbyint(x);
+    f *= 0x1p64;
+    f = nearbyint(f);
+    /* f in [-2^63, 2^63]; 2^63 wraps to the same u64 as -2^63 */
+    if (f >= 0x1p63) return 0x8000000000000000ull;
+    return (uint64_t)(int64_t)f;
+}
+
+/* add_backward_as_torus: poly += round(frac(IDFT(in) * conj(twist)) * 2^64) */
+void orc_fft_bwd_torus_add(uint64_t *poly, const double *in_c, int N)
+{
+    const plan_t *p = plan_for(N);
+    int n = p->n;
+    double re[512], im[512];
+    for (int j = 0; j < n; j++) {
+        re[j] = in_c[2 * j];
+        im[j] = in_c[2 * j + 1];
+    }
+    dft_bwd(p, re, im);
+    double inv = 1.0 / (double)n;
+    for (int j = 0; j < n; j++) {
+        double tr = p->twr[j], ti = -p->twi[j];
+        double a = (re[j] * tr - im[j] * ti) * inv;
+        double b = (re[j] * ti + im[j] * tr) * inv;
+        poly[j] += torus_from_double(a);
+        poly[j + n] += torus_from_double(b);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* polynomial / LWE helpers */
+
+/* tfhe fast_pbs_modulus_switch(x, N=1024, ModulusSwitchOffset(0), LutCountLog(3));
+ * call sites cbs_lib/src/pbs.rs:84-89,112-117 */
+uint64_t orc_modswitch(uint64_t x)
+{
+    const int log2N = 10;
+    uint64_t y = x >> (64 - log2N - 2 + ORC_LOG_LUT_COUNT);
+    y = (y + 1) >> 1;
+    return y << ORC_LOG_LUT_COUNT;
+}
+
+/* polynomial_wrapping_monic_monomial_mul: out = in * X^d mod (X^N + 1), d taken mod 2N
+ * (wrappers cbs_lib/src/utils.rs:322-396) */
+void orc_mono_mul(uint64_t *out, const uint64_t *in, int N, unsigned d)
+{
+    d %= (unsigned)(2 * N);
+    int neg = 0;
+    if (d >= (unsigned)N) {
+        d -= N;
+        neg = 1;
+    }
+    for (int j = 0; j < N; j++) {
+        uint64_t v;
+        if ((unsigned)j >= d) v = in[j - d];
+        else v = (uint64_t)0 - in[N + j - d];
+        out[j] = neg ? (uint64_t)0 - v : v;
+    }
+}
+
+static void mono_div(uint64_t *out, const uint64_t *in, int N, unsigned d)
+{
+    d %= (unsigned)(2 * N);
+    orc_mono_mul(out, in, N, (unsigned)(2 * N) - d);
+}
+
+/* eval_x_k_in_memory, cbs_lib/src/utils.rs:475-490 */
+void orc_eval_x_k(uint64_t *out, const uint64_t *in, int N, unsigned kappa)
+{
+    out[0] = in[0];
+    for (int i = 1; i < N; i++) {
+        unsigned long prod = (unsigned long)i * kappa;
+        int j = (int)(prod % (unsigned)N);
+        int neg = (int)((prod / (unsigned)N) & 1);
+        out[j] = neg ? (uint64_t)0 - in[i] : in[i];
+    }
+}
+
+/* tfhe extract_lwe_sample_from_glwe_ciphertext(glwe, lwe, MonomialDegree(t)) */
+void orc_sample_extract(uint64_t *lwe, const uint64_t *glwe, int k, int N, int t)
+{
+    for (int c = 0; c < k; c++) {
+        const uint64_t *m = glwe + (size_t)c * N;
+        uint64_t *o = lwe + (size_t)c * N;
+        for (int j = 0; j < N; j++) o[j] = (j <= t) ? m[t - j] : (uint64_t)0 - m[N + t - j];
+    }
+    lwe[(size_t)k * N] = glwe[(size_t)k * N + t];
+}
+
+/* convert_lwe_to_glwe_const, cbs_lib/src/glwe_conv.rs:12-44 */
+void orc_const_embed(uint64_t *glwe, const uint64_t *lwe, int k, int N)
+{
+    for (int c = 0; c < k; c++) {
+        const uint64_t *a = lwe + (size_t)c * N;
+        uint64_t *o = glwe + (size_t)c * N;
+        o[0] = a[0];
+        for (int j = 1; j < N; j++) o[j] = (uint64_t)0 - a[N - j];
+    }
+    uint64_t *body = glwe + (size_t)k * N;
+    memset(body, 0, sizeof(uint64_t) * N);
+    body[0] = lwe[(size_t)k * N];
+}
+
+/* tfhe SignedDecomposer: closest_representable + balanced digits, finest level first.
+ * Used directly at cbs_lib/src/fourier_glwe_keyswitch.rs:264-287 and inside
+ * add_external_product_assign. */
+void orc_decompose(int64_t *digits, const uint64_t *poly, int N, int base_log, int level)
+{
+    int nr = 64 - base_log * level;
+    uint64_t mask = ((uint64_t)1 << base_log) - 1;
+    for (int i = 0; i < N; i++) {
+        uint64_t x = poly[i];
+        uint64_t st = (x >> nr) + ((x >> (nr - 1)) & 1); /* closest_representable >> nr */
+        for (int t = 0; t < level; t++) {
+            uint64_t res = st & mask;
+            st >>= base_log;
+            uint64_t carry = (((res - 1) | st) & res) >> (base_log - 1);
+            st += carry;
+            digits[(size_t)t * N + i] = (int64_t)(res - (carry << base_log));
+        }
+    }
+}
+
+/* tfhe add_external_product_assign(out, ggsw_fourier, glwe); call sites cbs_lib/src/pbs.rs:138-144,
+ * cbs_lib/src/ggsw_conv.rs:189, src/bin/server_encrypted_aes_decryption.rs:575 */
+void orc_external_product_add(uint64_t *out, const double *ggsw_f, const uint64_t *glwe,
+                              int k, int N, int base_log, int level)
+{
+    int n = N / 2, ks = k + 1;
+    double *acc = calloc((size_t)ks * 2 * n, sizeof(double));
+    int64_t *digits = malloc(sizeof(int64_t) * (size_t)level * N);
+    double *f = malloc(sizeof(double) * 2 * n);
+    for (int r = 0; r < ks; r++) {
+        orc_decompose(digits, glwe + (size_t)r * N, N, base_log, level);
+        for (int t = 0; t < level; t++) {
+            int lev = level - 1 - t;
+            orc_fft_fwd_int(f, digits + (size_t)t * N, N);
+            for (int c = 0; c < ks; c++) {
+                const double *g = ggsw_f + (((size_t)lev * ks + r) * ks + c) * 2 * n;
+                double *a = acc + (size_t)c * 2 * n;
+                for (int j = 0; j < n; j++) {
+                    double fr = f[2 * j], fi = f[2 * j + 1], gr = g[2 * j], gi = g[2 * j + 1];
+                    a[2 * j] += fr * gr - fi * gi;
+                    a[2 * j + 1] += fr * gi + fi * gr;
+                }
+            }
+        }
+    }
+    for (int c = 0; c < ks; c++) orc_fft_bwd_torus_add(out + (size_t)c * N, acc + (size_t)c * 2 * n, N);
+    free(acc);
+    free(digits);
+    free(f);
+}
+
+/* tfhe convert_standard_ggsw_ciphertext_to_fourier: forward_as_torus of every polynomial */
+void orc_ggsw_to_fourier(double *out_f, const uint64_t *ggsw_std, int k, int N, int level)
+{
+    int polys = level * (k + 1) * (k + 1);
+    for (int p = 0; p < polys; p++) orc_fft_fwd_torus(out_f + (size_t)p * N, ggsw_std + (size_t)p * N, N);
+}
+
+/* ------------------------------------------------------------------------- */
+/* keys */
+struct orc_keys {
+    double *bsk_f;  /* [768][1][3][3][512] c64 */
+    double *ksk_f;  /* [8][3][4][128] c64  (Vanilla) */
+    double *auto_f; /* [10][2 in][2 split][3 lvl][3][512] c64 */
+    double *ss_f;   /* [2][2][3][3][512] c64 */
+};
+
+/* convert_standard_glwe_keyswitch_key_to_fourier, cbs_lib/src/fourier_glwe_keyswitch.rs:154-211 */
+static void ksk_to_fourier(double *out, const uint64_t *std, int in_k, int level, int out_size, int N,
+                           int split /* 0 = Vanilla */)
+{
+    int nsplit = split ? 2 : 1;
+    size_t glev_words = (size_t)level * out_size * N;
+    uint64_t *tmp = malloc(sizeof(uint64_t) * N);
+    for (int i = 0; i < in_k; i++) {
+        for (int s = 0; s < nsplit; s++) {
+            for (size_t p = 0; p < (size_t)level * out_size; p++) {
+                const uint64_t *src = std + i * glev_words + p * N;
+                for (int j = 0; j < N; j++) {
+                    uint64_t v = src[j];
+                    if (split) v = (s == 0) ? ((v << (64 - split)) >> (64 - split)) : (v >> split);
+                    tmp[j] = v;
+                }
+                orc_fft_fwd_torus(out + (((size_t)i * nsplit + s) * level * out_size + p) * N, tmp, N);
+            }
+        }
+    }
+    free(tmp);
+}
+
+orc_keys *orc_keys_create(const uint64_t *bsk, const uint64_t *ksk, const uint64_t *auto_std,
+                          const uint64_t *ss)
+{
+    orc_keys *K = calloc(1, sizeof(*K));
+    size_t bsk_polys = (size_t)ORC_LWE_N * ORC_PBS_LEVEL * 3 * 3;
+    K->bsk_f = malloc(sizeof(double) * bsk_polys * ORC_N);
+    /* convert_standard_lwe_bootstrap_key_to_fourier (server_encrypted_aes_decryption.rs:656-663) */
+#pragma omp parallel for schedule(static)
+    for (long p = 0; p < (long)bsk_polys; p++)
+        orc_fft_fwd_torus(K->bsk_f + (size_t)p * ORC_N, bsk + (size_t)p * ORC_N, ORC_N);
+    K->ksk_f = malloc(sizeof(double) * (size_t)ORC_KS_IN_K * ORC_KS_LEVEL * (ORC_KS_OUT_K + 1) * ORC_KS_N);
+    ksk_to_fourier(K->ksk_f, ksk, ORC_KS_IN_K, ORC_KS_LEVEL, ORC_KS_OUT_K + 1, ORC_KS_N, 0);
+    size_t auto_std_words = (size_t)ORC_K * ORC_AUTO_LEVEL * 3 * ORC_N;
+    size_t auto_f_doubles = (size_t)ORC_K * 2 * ORC_AUTO_LEVEL * 3 * ORC_N;
+    K->auto_f = malloc(sizeof(double) * ORC_NUM_AUTO * auto_f_doubles);
+    for (int a = 0; a < ORC_NUM_AUTO; a++)
+        ksk_to_fourier(K->auto_f + a * auto_f_doubles, auto_std + a * auto_std_words, ORC_K,
+                       ORC_AUTO_LEVEL, 3, ORC_N, ORC_AUTO_SPLIT);
+    size_t ss_polys = (size_t)ORC_K * ORC_SS_LEVEL * 3 * 3;
+    K->ss_f = malloc(sizeof(double) * ss_polys * ORC_N);
+    for (size_t p = 0; p < ss_polys; p++) orc_fft_fwd_torus(K->ss_f + p * ORC_N, ss + p * ORC_N, ORC_N);
+    return K;
+}
+
+void orc_keys_destroy(orc_keys *K)
+{
+    if (!K) return;
+    free(K->bsk_f);
+    free(K->ksk_f);
+    free(K->auto_f);
+    free(K->ss_f);
+    free(K);
+}
+
+/* ------------------------------------------------------------------------- */
+/* keyswitch_glwe_ciphertext, cbs_lib/src/fourier_glwe_keyswitch.rs:213-342.
+ * key_f layout [in_k][nsplit][level][out_size][N/2]; digits (finest first) are paired with the
+ * key's GLWE list reversed (:312). */
+static void glwe_keyswitch(uint64_t *out, const uint64_t *in, const double *key_f, int in_k, int out_size,
+                           int N, int base_log, int level, int split)
+{
+    int n = N / 2, nsplit = split ? 2 : 1;
+    memset(out, 0, sizeof(uint64_t) * (size_t)out_size * N);
+    memcpy(out + (size_t)(out_size - 1) * N, in + (size_t)in_k * N, sizeof(uint64_t) * N);
+    double *acc = calloc((size_t)nsplit * out_size * 2 * n, sizeof(double));
+    int64_t *digits = malloc(sizeof(int64_t) * (size_t)level * N);
+    double *f = malloc(sizeof(double) * 2 * n);
+    for (int i = 0; i < in_k; i++) {
+        orc_decompose(digits, in + (size_t)i * N, N, base_log, level);
+        for (int t = 0; t < level; t++) {
+            int lev = level - 1 - t;
+            orc_fft_fwd_int(f, digits + (size_t)t * N, N);
+            for (int s = 0; s < nsplit; s++) {
+                for (int c = 0; c < out_size; c++) {
+                    const double *g = key_f + ((((size_t)i * nsplit + s) * level + lev) * out_size + c) * 2 * n;
+                    double *a = acc + ((size_t)s * out_size + c) * 2 * n;
+                    /* update_with_fmadd, cbs_lib/src/fourier_poly_mult.rs:211-292 */
+                    for (int j = 0; j < n; j++) {
+                        double fr = f[2 * j], fi = f[2 * j + 1], gr = g[2 * j], gi = g[2 * j + 1];
+                        a[2 * j] += fr * gr - fi * gi;
+                        a[2 * j + 1] += fr * gi + fi * gr;
+                    }
+                }
+            }
+        }
+    }
+    uint64_t *buf = malloc(sizeof(uint64_t) * N);
+    for (int s = 0; s < nsplit; s++) {
+        int shift = (s == 0) ? 0 : split; /* :334-339 */
+        for (int c = 0; c < out_size; c++) {
+            memset(buf, 0, sizeof(uint64_t) * N);
+            orc_fft_bwd_torus_add(buf, acc + ((size_t)s * out_size + c) * 2 * n, N);
+            uint64_t *o = out + (size_t)c * N;
+            for (int j = 0; j < N; j++) o[j] += buf[j] << shift;
+        }
+    }
+    free(buf);
+    free(acc);
+    free(digits);
+    free(f);
+}
+
+/* keyswitch_lwe_ciphertext_by_glwe_keyswitch, cbs_lib/src/fourier_glwe_keyswitch.rs:344-379 */
+void orc_lwe_keyswitch(const orc_keys *K, const uint64_t *in2049, uint64_t *out769)
+{
+    uint64_t gin[(ORC_KS_IN_K + 1) * ORC_KS_N], gout[(ORC_KS_OUT_K + 1) * ORC_KS_N];
+    orc_const_embed(gin, in2049, ORC_KS_IN_K, ORC_KS_N);
+    glwe_keyswitch(gout, gin, K->ksk_f, ORC_KS_IN_K, ORC_KS_OUT_K + 1, ORC_KS_N, ORC_KS_BASE_LOG,
+                   ORC_KS_LEVEL, 0);
+    orc_sample_extract(out769, gout, ORC_KS_OUT_K, ORC_KS_N, 0);
+}
+
+/* accumulator of lwe_msb_bit_to_glev_by_trace_with_preprocessing (cbs_lib/src/ggsw_conv.rs:250-268)
+ * followed by gen_blind_rotate_local_assign (cbs_lib/src/pbs.rs:70-161) */
+void orc_blind_rotate(const orc_keys *K, const uint64_t *lwe, uint64_t *acc)
+{
+    const int N = ORC_N, lut_count = 1 << ORC_LOG_LUT_COUNT;
+    uint64_t A[ORC_N], tmp[ORC_N];
+    for (int i = 0; i < N; i++) {
+        int k = i % lut_count;
+        int log_scale = 64 - (k + 1) * ORC_CBS_BASE_LOG;
+        A[i] = ((uint64_t)0 - 1) << (log_scale - 1);
+    }
+    for (int i = 0; i < N / 2; i++) A[i] = (uint64_t)0 - A[i];
+    /* rotate_left(N/2) */
+    memcpy(tmp, A + N / 2, sizeof(uint64_t) * (N / 2));
+    memcpy(tmp + N / 2, A, sizeof(uint64_t) * (N / 2));
+    memset(acc, 0, sizeof(uint64_t) * ORC_K * N);
+    /* pbs.rs:84-101: acc <- acc * X^{-b~} */
+    mono_div(acc + (size_t)ORC_K * N, tmp, N, (unsigned)orc_modswitch(lwe[ORC_LWE_N]));
+    uint64_t ct1[ORC_GLWE_WORDS];
+    const size_t ggsw_doubles = (size_t)ORC_PBS_LEVEL * 3 * 3 * ORC_N;
+    for (int i = 0; i < ORC_LWE_N; i++) {
+        if (lwe[i] == 0) continue; /* pbs.rs:111 */
+        unsigned d = (unsigned)orc_modswitch(lwe[i]);
+        for (int p = 0; p < ORC_K + 1; p++) {
+            /* polynomial_wrapping_monic_monomial_mul_and_subtract, utils.rs:503-568 */
+            orc_mono_mul(ct1 + (size_t)p * N, acc + (size_t)p * N, N, d);
+            for (int j = 0; j < N; j++) ct1[(size_t)p * N + j] -= acc[(size_t)p * N + j];
+        }
+        orc_external_product_add(acc, K->bsk_f + (size_t)i * ggsw_doubles, ct1, ORC_K, N, ORC_PBS_BASE_LOG,
+                                 ORC_PBS_LEVEL);
+    }
+}
+
+/* cbs_lib/src/ggsw_conv.rs:302-314 (everything between the blind rotation and the trace):
+ * monomial div by X^k, + 2^(log_scale-1), sample extract 0, lwe_preprocessing_assign
+ * (cbs_lib/src/mod_switch.rs:52-74 == logical >> log2 N), convert_lwe_to_glwe_const */
+void orc_glev_from_acc(const uint64_t *acc, uint64_t *glev_pre)
+{
+    const int N = ORC_N;
+    uint64_t buf[ORC_GLWE_WORDS], lwe[ORC_BIG_N + 1];
+    for (int k = 0; k < ORC_CBS_LEVEL; k++) {
+        int cur_level = k + 1;
+        int log_scale = 64 - cur_level * ORC_CBS_BASE_LOG;
+        for (int p = 0; p < ORC_K + 1; p++) mono_div(buf + (size_t)p * N, acc + (size_t)p * N, N, (unsigned)k);
+        buf[(size_t)ORC_K * N] += (uint64_t)1 << (log_scale - 1);
+        orc_sample_extract(lwe, buf, ORC_K, N, 0);
+        for (int j = 0; j < ORC_BIG_N + 1; j++) {
+            uint64_t v = lwe[j];
+            v = v - (v % ((uint64_t)1 << 10)); /* mod switch to 2^54 */
+            lwe[j] = v / ((uint64_t)1 << 10);  /* mod raise */
+        }
+        orc_const_embed(glev_pre + (size_t)k * ORC_GLWE_WORDS, lwe, ORC_K, N);
+    }
+}
+
+static unsigned auto_kappa(int i /* 1..10 */) { return (unsigned)(ORC_N / (1 << (i - 1)) + 1); }
+
+/* AutomorphKey::auto, cbs_lib/src/automorphism.rs:134-149 */
+void orc_auto_step(const orc_keys *K, int i, const uint64_t *in, uint64_t *out)
+{
+    uint64_t pw[ORC_GLWE_WORDS];
+    unsigned kappa = auto_kappa(i);
+    for (int p = 0; p < ORC_K + 1; p++) orc_eval_x_k(pw + (size_t)p * ORC_N, in + (size_t)p * ORC_N, ORC_N, kappa);
+    const size_t auto_f_doubles = (size_t)ORC_K * 2 * ORC_AUTO_LEVEL * 3 * ORC_N;
+    glwe_keyswitch(out, pw, K->auto_f + (size_t)(i - 1) * auto_f_doubles, ORC_K, ORC_K + 1, ORC_N,
+                   ORC_AUTO_BASE_LOG, ORC_AUTO_LEVEL, ORC_AUTO_SPLIT);
+}
+
+/* trace_assign -> trace_partial_assign(n = 1), cbs_lib/src/automorphism.rs:195-233 */
+void orc_trace(const orc_keys *K, uint64_t *glwe)
+{
+    uint64_t buf[ORC_GLWE_WORDS];
+    for (int i = 1; i <= 10; i++) {
+        orc_auto_step(K, i, glwe, buf);
+        for (int j = 0; j < ORC_GLWE_WORDS; j++) glwe[j] += buf[j];
+    }
+}
+
+/* switch_scheme, cbs_lib/src/ggsw_conv.rs:163-193 */
+void orc_scheme_switch(const orc_keys *K, const uint64_t *glev, uint64_t *ggsw)
+{
+    const size_t ss_doubles = (size_t)ORC_SS_LEVEL * 3 * 3 * ORC_N;
+    memset(ggsw, 0, sizeof(uint64_t) * ORC_GGSW_WORDS);
+    for (int col = 0; col < ORC_CBS_LEVEL; col++) {
+        const uint64_t *g = glev + (size_t)col * ORC_GLWE_WORDS;
+        uint64_t *rows = ggsw + (size_t)col * 3 * ORC_GLWE_WORDS;
+        for (int i = 0; i < ORC_K; i++)
+            orc_external_product_add(rows + (size_t)i * ORC_GLWE_WORDS, K->ss_f + (size_t)i * ss_doubles, g, ORC_K,
+                                     ORC_N, ORC_SS_BASE_LOG, ORC_SS_LEVEL);
+        memcpy(rows + (size_t)ORC_K * ORC_GLWE_WORDS, g, sizeof(uint64_t) * ORC_GLWE_WORDS);
+    }
+}
+
+/* lwe_msb_bit_to_glev_by_trace_with_preprocessing (ggsw_conv.rs:231-318) + switch_scheme */
+void orc_circuit_bootstrap(const orc_keys *K, const uint64_t *lwe769, uint64_t *ggsw_std)
+{
+    uint64_t acc[ORC_GLWE_WORDS];
+    uint64_t *glev = malloc(sizeof(uint64_t) * ORC_CBS_LEVEL * ORC_GLWE_WORDS);
+    orc_blind_rotate(K, lwe769, acc);
+    orc_glev_from_acc(acc, glev);
+    for (int l = 0; l < ORC_CBS_LEVEL; l++) orc_trace(K, glev + (size_t)l * ORC_GLWE_WORDS);
+    orc_scheme_switch(K, glev, ggsw_std);
+    free(glev);
+}
+
+/* evaluate_8_to_8_cipher_lut, src/bin/server_encrypted_aes_decryption.rs:550-588 */
+void orc_lut8_eval(const double *ggsw_f8, const uint64_t *lut, uint64_t *out)
+{
+    const int N = ORC_N;
+    const size_t ggsw_doubles = (size_t)ORC_CBS_LEVEL * 3 * 3 * ORC_N;
+    uint64_t acc[ORC_GLWE_WORDS], buf[ORC_GLWE_WORDS];
+    for (int a = 0; a < 2; a++) {
+        memcpy(acc, lut + (size_t)a * ORC_GLWE_WORDS, sizeof(acc));
+        for (int i = 0; i < 8; i++) {
+            for (int p = 0; p < ORC_K + 1; p++) {
+                mono_div(buf + (size_t)p * N, acc + (size_t)p * N, N, 1u << i);
+                for (int j = 0; j < N; j++) buf[(size_t)p * N + j] -= acc[(size_t)p * N + j];
+            }
+            orc_external_product_add(acc, ggsw_f8 + (size_t)i * ggsw_doubles, buf, ORC_K, N, ORC_CBS_BASE_LOG,
+                                     ORC_CBS_LEVEL);
+        }
+        for (int t = 0; t < 4; t++)
+            orc_sample_extract(out + (size_t)(4 * a + t) * (ORC_BIG_N + 1), acc, ORC_K, N, t * 256);
+    }
+}
+
+/* known_rotate_keyed_lut, cbs_lib/src/aes_he.rs:64-93 */
+void orc_known_rotate(const uint8_t *ct16, const uint64_t *luts, uint64_t *state)
+{
+    for (int i = 0; i < 128; i++) {
+        int byte_idx = i / 8, bit_idx = i % 8;
+        int acc_idx = bit_idx / 4, lut_idx = bit_idx % 4;
+        int deg = lut_idx * 256 + ct16[byte_idx];
+        orc_sample_extract(state + (size_t)i * (ORC_BIG_N + 1), luts + ((size_t)byte_idx * 2 + acc_idx) * ORC_GLWE_WORDS,
+                           ORC_K, ORC_N, deg);
+    }
+}
+
+#define LWE_W (ORC_BIG_N + 1)
+static uint64_t *state_byte(uint64_t *st, int row, int col) /* aes_he.rs:322-346 */
+{
+    return st + (size_t)8 * (4 * col + row) * LWE_W;
+}
+static const uint64_t *state_byte_c(const uint64_t *st, int row, int col)
+{
+    return st + (size_t)8 * (4 * col + row) * LWE_W;
+}
+
+/* he_inv_mix_columns_precomp, src/bin/server_encrypted_aes_decryption.rs:195-243 */
+void orc_inv_mix_columns_precomp(uint64_t *st, const uint64_t *t9, const uint64_t *t11, const uint64_t *t13,
+                                 const uint64_t *t14)
+{
+    for (int row = 0; row < 4; row++) {
+        for (int col = 0; col < 4; col++) {
+            uint64_t *d = state_byte(st, row, col);
+            const uint64_t *a = state_byte_c(t14, row, col);
+            const uint64_t *b = state_byte_c(t11, (row + 1) % 4, col);
+            const uint64_t *c = state_byte_c(t13, (row + 2) % 4, col);
+            const uint64_t *e = state_byte_c(t9, (row + 3) % 4, col);
+            for (int j = 0; j < 8 * LWE_W; j++) d[j] = a[j] + b[j] + c[j] + e[j];
+        }
+    }
+}
+
+/* he_inv_shift_rows, src/bin/server_encrypted_aes_decryption.rs:245-265 */
+void orc_inv_shift_rows(uint64_t *st)
+{
+    uint64_t *buf = malloc(sizeof(uint64_t) * 128 * LWE_W);
+    memcpy(buf, st, sizeof(uint64_t) * 128 * LWE_W);
+    for (int row = 1; row < 4; row++)
+        for (int col = 0; col < 4; col++)
+            memcpy(state_byte(st, row, col), state_byte_c(buf, row, (4 - row + col) % 4), sizeof(uint64_t) * 8 * LWE_W);
+    free(buf);
+}
+
+/* he_inv_keyed_sbox_8_to_32_eval_by_patched_wwlp_cbs / ..._8_to_8_... for one byte,
+ * src/bin/server_encrypted_aes_decryption.rs:350-548 */
+static void sbox_byte(const orc_keys *K, const uint64_t *in8x769, int nluts, const uint64_t *const *luts,
+                      uint64_t *const *outs)
+{
+    uint64_t *ggsw = malloc(sizeof(uint64_t) * ORC_GGSW_WORDS);
+    double *ggsw_f = malloc(sizeof(double) * 8 * ORC_GGSW_WORDS);
+    for (int b = 0; b < 8; b++) {
+        orc_circuit_bootstrap(K, in8x769 + (size_t)b * (ORC_LWE_N + 1), ggsw);
+        orc_ggsw_to_fourier(ggsw_f + (size_t)b * ORC_GGSW_WORDS, ggsw, ORC_K, ORC_N, ORC_CBS_LEVEL);
+    }
+    for (int m = 0; m < nluts; m++) orc_lut8_eval(ggsw_f, luts[m], outs[m]);
+    free(ggsw);
+    free(ggsw_f);
+}
+
+/* aes_to_lwe_trasnciphering, src/bin/server_encrypted_aes_decryption.rs:28-191, for nblocks blocks */
+void orc_aes128_transcipher(const orc_keys *K, const uint8_t *ct, int nblocks, const uint64_t *k10_9,
+                            const uint64_t *k8_1, const uint64_t *k0, uint64_t *out)
+{
+    const size_t ST = (size_t)128 * LWE_W;
+    const size_t MULT = (size_t)16 * 2 * ORC_GLWE_WORDS; /* one multiple's LUT set */
+    uint64_t *st = out;
+    uint64_t *t = malloc(sizeof(uint64_t) * 4 * ST * nblocks);
+    uint64_t *ks = malloc(sizeof(uint64_t) * (size_t)128 * (ORC_LWE_N + 1) * nblocks);
+    for (int blk = 0; blk < nblocks; blk++) {
+        /* cleartext inv_shift_rows of the AES ciphertext (:89-91, :590-597) */
+        uint8_t c2[16];
+        for (int col = 0; col < 4; col++)
+            for (int row = 0; row < 4; row++) c2[4 * col + row] = ct[16 * blk + 4 * ((4 + col - row) % 4) + row];
+        uint64_t *tb = t + (size_t)blk * 4 * ST;
+        for (int m = 0; m < 4; m++) orc_known_rotate(c2, k10_9 + (size_t)m * MULT, tb + (size_t)m * ST);
+        orc_inv_mix_columns_precomp(st + blk * ST, tb, tb + ST, tb + 2 * ST, tb + 3 * ST);
+        orc_inv_shift_rows(st + blk * ST);
+    }
+    for (int round = 8; round >= 0; round--) {
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long i = 0; i < (long)nblocks * 128; i++)
+            orc_lwe_keyswitch(K, st + (size_t)i * LWE_W, ks + (size_t)i * (ORC_LWE_N + 1));
+#pragma omp parallel for schedule(dynamic, 1)
+        for (long job = 0; job < (long)nblocks * 16; job++) {
+            int blk = (int)(job / 16), byte = (int)(job % 16);
+            const uint64_t *in = ks + ((size_t)blk * 128 + 8 * byte) * (ORC_LWE_N + 1);
+            if (round >= 1) {
+                const uint64_t *luts[4];
+                uint64_t *outs[4];
+                for (int m = 0; m < 4; m++) {
+                    luts[m] = k8_1 + (((size_t)(round - 1) * 4 + m) * 16 + byte) * 2 * ORC_GLWE_WORDS;
+                    outs[m] = t + (size_t)blk * 4 * ST + (size_t)m * ST + (size_t)8 * byte * LWE_W;
+                }
+                sbox_byte(K, in, 4, luts, outs);
+            } else {
+                const uint64_t *luts[1] = {k0 + (size_t)byte * 2 * ORC_GLWE_WORDS};
+                uint64_t *outs[1] = {st + blk * ST + (size_t)8 * byte * LWE_W};
+                sbox_byte(K, in, 1, luts, outs);
+            }
+        }
+        if (round >= 1) {
+            for (int blk = 0; blk < nblocks; blk++) {
+                uint64_t *tb = t + (size_t)blk * 4 * ST;
+                orc_inv_mix_columns_precomp(st + blk * ST, tb, tb + ST, tb + 2 * ST, tb + 3 * ST);
+                orc_inv_shift_rows(st + blk * ST);
+            }
+        }
+    }
+    /* :182-189 reverse the 8 LWE of every byte -> MSB first */
+    uint64_t tmp[LWE_W];
+    for (long byte = 0; byte < (long)nblocks * 16; byte++) {
+        uint64_t *b = st + (size_t)8 * byte * LWE_W;
+        for (int i = 0; i < 4; i++) {
+            memcpy(tmp, b + (size_t)i * LWE_W, sizeof(tmp));
+            memcpy(b + (size_t)i * LWE_W, b + (size_t)(7 - i) * LWE_W, sizeof(tmp));
+            memcpy(b + (size_t)(7 - i) * LWE_W, tmp, sizeof(tmp));
+        }
+    }
+    free(t);
+    free(ks);
+}
+
+/* tfhe cmux_assign(ct0, ct1, ggsw): ct1 -= ct0; ct0 += ggsw (x) ct1 */
+static void cmux(uint64_t *ct0, uint64_t *ct1, const double *ggsw_f)
+{
+    for (int j = 0; j < ORC_GLWE_WORDS; j++) ct1[j] -= ct0[j];
+    orc_external_product_add(ct0, ggsw_f, ct1, ORC_K, ORC_N, ORC_CBS_BASE_LOG, ORC_CBS_LEVEL);
+}
+
+/* max_of_two, src/bin/server_encrypted_compute.rs:34-98 */
+void orc_max_of_two(const uint64_t *ggsw_a, const uint64_t *ggsw_b, const uint64_t *lwe_a, const uint64_t *lwe_b,
+                    uint64_t *out, int reset_e)
+{
+    double *fa = malloc(sizeof(double) * 16 * ORC_GGSW_WORDS), *fb = malloc(sizeof(double) * 16 * ORC_GGSW_WORDS);
+    for (int i = 0; i < 16; i++) {
+        orc_ggsw_to_fourier(fa + (size_t)i * ORC_GGSW_WORDS, ggsw_a + (size_t)i * ORC_GGSW_WORDS, ORC_K, ORC_N, ORC_CBS_LEVEL);
+        orc_ggsw_to_fourier(fb + (size_t)i * ORC_GGSW_WORDS, ggsw_b + (size_t)i * ORC_GGSW_WORDS, ORC_K, ORC_N, ORC_CBS_LEVEL);
+    }
+    uint64_t ga[ORC_GLWE_WORDS], gb[ORC_GLWE_WORDS], ge[ORC_GLWE_WORDS], m0[ORC_GLWE_WORDS], m1[ORC_GLWE_WORDS],
+        tmp[ORC_GLWE_WORDS];
+    memset(ge, 0, sizeof(ge));
+    for (int j = 0; j < 16; j++) {
+        if (reset_e) memset(ge, 0, sizeof(ge));
+        orc_const_embed(gb, lwe_a + (size_t)j * LWE_W, ORC_K, ORC_N); /* :78  (glwe_b <- lwe_a) */
+        orc_const_embed(ga, lwe_b + (size_t)j * LWE_W, ORC_K, ORC_N); /* :79  (glwe_a <- lwe_b) */
+        for (int i = 15; i >= 0; i--) {                              /* .rev(): LSB -> MSB */
+            memcpy(m0, ge, sizeof(ge));
+            memcpy(tmp, ga, sizeof(ga));
+            cmux(m0, tmp, fb + (size_t)i * ORC_GGSW_WORDS);
+            memcpy(m1, gb, sizeof(gb));
+            memcpy(tmp, ge, sizeof(ge));
+            cmux(m1, tmp, fb + (size_t)i * ORC_GGSW_WORDS);
+            memcpy(ge, m0, sizeof(ge));
+            cmux(ge, m1, fa + (size_t)i * ORC_GGSW_WORDS);
+        }
+        orc_sample_extract(out + (size_t)j * LWE_W, ge, ORC_K, ORC_N, 0);
+    }
+    free(fa);
+    free(fb);
+}
+
+/* main of src/bin/server_encrypted_compute.rs:203-350, generalised from 8 to nvals values
+ * (sequential fold: running max vs chunk i, running max re-bootstrapped each time) */
+void orc_max_u16(const orc_keys *K, const uint64_t *in, int nvals, uint64_t *out)
+{
+    uint64_t *ggsw = malloc(sizeof(uint64_t) * (size_t)nvals * 16 * ORC_GGSW_WORDS);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long i = 0; i < (long)nvals * 16; i++) {
+        uint64_t ks[ORC_LWE_N + 1];
+        orc_lwe_keyswitch(K, in + (size_t)i * LWE_W, ks);
+        orc_circuit_bootstrap(K, ks, ggsw + (size_t)i * ORC_GGSW_WORDS);
+    }
+    uint64_t *mid = malloc(sizeof(uint64_t) * 16 * LWE_W), *mid2 = malloc(sizeof(uint64_t) * 16 * LWE_W);
+    uint64_t *mid_ggsw = malloc(sizeof(uint64_t) * 16 * ORC_GGSW_WORDS);
+    if (nvals == 1) {
+        memcpy(out, in, sizeof(uint64_t) * 16 * LWE_W);
+    } else {
+        orc_max_of_two(ggsw, ggsw + (size_t)16 * ORC_GGSW_WORDS, in, in + (size_t)16 * LWE_W, mid2, 0);
+        for (int i = 2; i < nvals; i++) {
+            memcpy(mid, mid2, sizeof(uint64_t) * 16 * LWE_W);
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int b = 0; b < 16; b++) {
+                uint64_t ks[ORC_LWE_N + 1];
+                orc_lwe_keyswitch(K, mid + (size_t)b * LWE_W, ks);
+                orc_circuit_bootstrap(K, ks, mid_ggsw + (size_t)b * ORC_GGSW_WORDS);
+            }
+            orc_max_of_two(mid_ggsw, ggsw + (size_t)i * 16 * ORC_GGSW_WORDS, mid, in + (size_t)i * 16 * LWE_W, mid2, 0);
+        }
+        memcpy(out, mid2, sizeof(uint64_t) * 16 * LWE_W);
+    }
+    free(ggsw);
+    free(mid);
+    free(mid2);
+    free(mid_ggsw);
+}
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
