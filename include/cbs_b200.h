@@ -1,0 +1,173 @@
+/*
+ * cbs_b200.h — C ABI of libcbs_b200.so: the B200 (sm_100a) implementation of the server-side hot
+ * path of code-perspective/temp-fhe-transciphering (AES-128 transciphering over bit-wise TFHE
+ * ciphertexts with the cbs_lib circuit-bootstrapping pipeline, parameter set AES_TIGHT,
+ * submission/cbs_lib/src/aes_instances.rs:76-97).
+ *
+ * The reference has no FFI of its own: its boundary is (1) the stage executables' file contract and
+ * (2) cbs_lib's public Rust functions.  This header is what a Rust `-sys` crate
+ * (cc/bindgen) would bind; INTEGRATION.md shows that binding next to each cbs_lib function it
+ * replaces.  Plain pointers and sizes only; every call returns 0 on success, non-zero on error
+ * (cbs_last_error() gives the message); the caller owns all host buffers, a context owns all device
+ * memory; one context may be used from one host thread at a time.  There is NO CPU fallback: every
+ * compute entry point fails with CBS_ERR_CUDA if no sm_100 device / kernel image is available.
+ *
+ * Array layouts (little-endian u64, wrapping arithmetic; same flat layouts the reference's
+ * containers hold):
+ *   LWE small   [768 mask][body]                         769 words
+ *   LWE big     [2048 mask][body]                        2049 words
+ *   GLWE        [2 mask polys][body] x 1024              3072 words
+ *   GLEV        [7 levels] GLWE                          21504 words
+ *   GGSW        [7 levels][3 rows][3 polys][1024]        64512 words  (level 1 = coarsest first)
+ *   bsk         [768][1][3][3][1024]      ksk [8][3][4][256]      ss [2][2][3][3][1024]
+ *   auto        [10][2][3][3][1024] standard-domain GLWE keyswitch keys, index i <-> X -> X^((1024>>i)+1)
+ *   k10_9       [4 (x9,x11,x13,x14)][16 bytes][2 acc] GLWE
+ *   k8_1        [8 (round-1)][4][16][2] GLWE              k0 [16][2] GLWE
+ */
+#ifndef CBS_B200_H
+#define CBS_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBS_OK          0
+#define CBS_ERR_ARG     1
+#define CBS_ERR_IO      2
+#define CBS_ERR_FORMAT  3
+#define CBS_ERR_CUDA    4
+#define CBS_ERR_NOMEM   5
+
+#define CBS_LWE_SMALL_WORDS 769
+#define CBS_LWE_BIG_WORDS   2049
+#define CBS_GLWE_WORDS      3072
+#define CBS_GLEV_WORDS      21504
+#define CBS_GGSW_WORDS      64512
+#define CBS_BSK_WORDS       (768u * 9u * 1024u)
+#define CBS_KSK_WORDS       (8u * 3u * 4u * 256u)
+#define CBS_AUTO_WORDS      (10u * 2u * 3u * 3u * 1024u)
+#define CBS_SS_WORDS        (2u * 2u * 3u * 3u * 1024u)
+#define CBS_K10_9_WORDS     (4u * 16u * 2u * 3072u)
+#define CBS_K8_1_WORDS      (8u * 4u * 16u * 2u * 3072u)
+#define CBS_K0_WORDS        (16u * 2u * 3072u)
+
+typedef struct cbs_keyset cbs_keyset; /* host-side key material, standard domain */
+typedef struct cbs_ctx cbs_ctx;       /* one GPU: Fourier-domain keys + workspaces */
+
+const char *cbs_last_error(void);
+const char *cbs_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Key material and the io/ file formats (bincode 1.3).
+ * Replaces the deserialisation block of both server mains
+ * (src/bin/server_encrypted_aes_decryption.rs:619-643, src/bin/server_encrypted_compute.rs:131-201). */
+
+/* read io_dir/public_keys/{bsk,ksk,auto_keys,ss_key}.bin; with_secret != 0 also reads
+ * io_dir/secret_keys/{lwe_sk,glwe_sk}.bin (tests / client side only). */
+int cbs_keyset_load_dir(const char *io_dir, int with_secret, cbs_keyset **out);
+/* write the same files (auto_keys.bin in the reference's Fourier split-limb form). */
+int cbs_keyset_save_dir(const cbs_keyset *ks, const char *io_dir, int with_secret);
+/* adopt caller-provided standard-domain arrays (copied). secret keys may be NULL. */
+int cbs_keyset_from_arrays(const uint64_t *bsk, const uint64_t *ksk, const uint64_t *auto_std, const uint64_t *ss,
+                           const uint64_t *lwe_sk_small /*768 or NULL*/, const uint64_t *glwe_sk /*2048 or NULL*/,
+                           cbs_keyset **out);
+/* Seeded client-side key generation with the reference's distributions (binary secrets, Gaussian
+ * noise; cbs_lib/src/keygen.rs:187-243, src/bin/client_key_generation.rs:20-86).  Client-side helper
+ * for tests and benches: the reference's own keygen is unseeded. */
+int cbs_keyset_generate(uint64_t seed, cbs_keyset **out);
+void cbs_keyset_free(cbs_keyset *ks);
+const uint64_t *cbs_keyset_bsk(const cbs_keyset *ks);
+const uint64_t *cbs_keyset_ksk(const cbs_keyset *ks);
+const uint64_t *cbs_keyset_auto(const cbs_keyset *ks);
+const uint64_t *cbs_keyset_ss(const cbs_keyset *ks);
+const uint64_t *cbs_keyset_lwe_sk_small(const cbs_keyset *ks); /* NULL if absent */
+const uint64_t *cbs_keyset_glwe_sk(const cbs_keyset *ks);      /* NULL if absent; == big LWE key */
+
+/* AllRdKeys (src/data_struct.rs:11-26) <-> flat arrays. */
+int cbs_trans_key_load(const char *path, uint64_t *k10_9, uint64_t *k8_1, uint64_t *k0);
+int cbs_trans_key_save(const char *path, const uint64_t *k10_9, const uint64_t *k8_1, const uint64_t *k0);
+/* client_encode_encrypt equivalent (src/bin/client_encode_encrypt.rs:9-22, src/data_struct.rs:30-269):
+ * rounds 10/9 encrypted LUTs, rounds 8..1 and 0 trivial LUTs, for ECB block decryption. */
+int cbs_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *k10_9,
+                           uint64_t *k8_1, uint64_t *k0);
+/* LweCiphertextList<Vec<u64>> result.bin */
+int cbs_lwe_list_load(const char *path, uint64_t **data /* malloc'd, free with cbs_free */, uint64_t *count,
+                      uint64_t *lwe_words);
+int cbs_lwe_list_save(const char *path, const uint64_t *data, uint64_t count, uint64_t lwe_words);
+void cbs_free(void *p);
+/* encrypt bits (0/1) at delta = 2^63 under the big LWE key (tests / microbench inputs) */
+int cbs_encrypt_bits_big(const cbs_keyset *ks, const uint8_t *bits, int count, uint64_t seed, uint64_t *out);
+/* ... and under the small (768) key, input format of the blind rotation */
+int cbs_encrypt_bits_small(const cbs_keyset *ks, const uint8_t *bits, int count, uint64_t seed, uint64_t *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device context: uploads the keys, converts them to the Fourier domain ON THE GPU
+ * (replaces server_encrypted_aes_decryption.rs:645-687). */
+int cbs_device_count(int *count); /* visible CUDA devices (CBS_ERR_CUDA if the driver is absent) */
+int cbs_ctx_create(const cbs_keyset *ks, int device, cbs_ctx **out);
+void cbs_ctx_destroy(cbs_ctx *ctx);
+int cbs_ctx_device(const cbs_ctx *ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches claim) */
+uint64_t cbs_ctx_launch_count(const cbs_ctx *ctx);
+/* make the context issue its work on an existing CUDA stream (cudaStream_t as void*); NULL = own stream */
+int cbs_ctx_set_stream(cbs_ctx *ctx, void *cuda_stream);
+int cbs_ctx_synchronize(cbs_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched stage entry points, HOST buffers (H2D + kernels + D2H inside the call).
+ * Each mirrors one cbs_lib function, applied to `count` independent ciphertexts. */
+
+/* keyswitch_lwe_ciphertext_by_glwe_keyswitch, cbs_lib/src/fourier_glwe_keyswitch.rs:344 */
+int cbs_lwe_keyswitch(cbs_ctx *ctx, const uint64_t *in_big, uint64_t *out_small, int count);
+/* accumulator + gen_blind_rotate_local_assign, cbs_lib/src/ggsw_conv.rs:250-300, pbs.rs:70 */
+int cbs_blind_rotate(cbs_ctx *ctx, const uint64_t *in_small, uint64_t *acc_out, int count);
+/* cbs_lib/src/ggsw_conv.rs:302-314 (everything between blind rotation and trace) */
+int cbs_glev_from_acc(cbs_ctx *ctx, const uint64_t *acc, uint64_t *glev_out, int count);
+/* trace_assign, cbs_lib/src/automorphism.rs:195 — in place on `count` GLWE */
+int cbs_trace(cbs_ctx *ctx, uint64_t *glwe_inout, int count);
+/* lwe_msb_bit_to_glev_by_trace_with_preprocessing, cbs_lib/src/ggsw_conv.rs:231 */
+int cbs_lwe_msb_bit_to_glev(cbs_ctx *ctx, const uint64_t *in_small, uint64_t *glev_out, int count);
+/* switch_scheme, cbs_lib/src/ggsw_conv.rs:163 */
+int cbs_scheme_switch(cbs_ctx *ctx, const uint64_t *glev, uint64_t *ggsw_out, int count);
+/* circuit_bootstrap_lwe_ciphertext_by_trace_with_preprocessing, cbs_lib/src/ggsw_conv.rs:409
+ * (output in the standard domain; the Fourier form stays on the device) */
+int cbs_circuit_bootstrap(cbs_ctx *ctx, const uint64_t *in_small, uint64_t *ggsw_out, int count);
+/* evaluate_8_to_8_cipher_lut, src/bin/server_encrypted_aes_decryption.rs:550: nbytes groups of 8 GGSW
+ * bits (LSB first), nluts LUTs per byte, each LUT = 2 GLWE accumulators;
+ * out[nbytes][nluts][8] big LWE, bit 4*a + t of accumulator a. */
+int cbs_lut8_eval(cbs_ctx *ctx, const uint64_t *ggsw_bits, int nbytes, const uint64_t *luts, int nluts, uint64_t *out);
+/* known_rotate_keyed_lut x4 + he_inv_mix_columns_precomp + he_inv_shift_rows
+ * (cbs_lib/src/aes_he.rs:64, server_encrypted_aes_decryption.rs:89-128): first two rounds */
+int cbs_aes_first_rounds(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const uint64_t *k10_9, uint64_t *state_out);
+/* he_inv_mix_columns_precomp + he_inv_shift_rows on t4 = [4 (x9,x11,x13,x14)][nblocks][128] big LWE */
+int cbs_aes_inv_linear(cbs_ctx *ctx, const uint64_t *t4, int nblocks, uint64_t *state_out);
+
+/* aes_to_lwe_trasnciphering, src/bin/server_encrypted_aes_decryption.rs:28-191, for nblocks
+ * independent 16-byte ECB blocks.  out[nblocks][128] big LWE, MSB-first inside each byte
+ * (the exact payload of ciphertext_aes_download/result.bin). */
+int cbs_aes128_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const uint64_t *k10_9, const uint64_t *k8_1,
+                           const uint64_t *k0, uint64_t *out);
+/* stage 8, src/bin/server_encrypted_compute.rs:99-359: encrypted max of nvals 16-bit values
+ * (in[nvals][16] big LWE, MSB first) -> out[16] big LWE.  The reference accepts exactly 8 values
+ * (sequential fold); any nvals >= 1 is reduced as a balanced tree here. */
+int cbs_max_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-resident variants (inputs/outputs already in HBM, asynchronous on the context's stream).
+ * Used by bench.py's `value` leg and by callers that keep state on the GPU. */
+int cbs_trans_key_upload(cbs_ctx *ctx, const uint64_t *k10_9, const uint64_t *k8_1, const uint64_t *k0);
+int cbs_aes128_transcipher_dev(cbs_ctx *ctx, const uint8_t *d_ct, int nblocks, uint64_t *d_out);
+int cbs_circuit_bootstrap_dev(cbs_ctx *ctx, const uint64_t *d_in_small, int count);  /* GGSW stays in the workspace */
+int cbs_blind_rotate_dev(cbs_ctx *ctx, const uint64_t *d_in_small, uint64_t *d_acc_out, int count);
+/* plain device buffers for callers without their own allocator */
+int cbs_dev_alloc(cbs_ctx *ctx, size_t bytes, void **dptr);
+int cbs_dev_free(cbs_ctx *ctx, void *dptr);
+int cbs_dev_upload(cbs_ctx *ctx, void *dptr, const void *host, size_t bytes);
+int cbs_dev_download(cbs_ctx *ctx, void *host, const void *dptr, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,356 @@
+"""temp_fhe_transciphering_b200 — host-side mirror of the reference's cbs_lib interface over
+libcbs_b200.so (hand-written sm_100a kernels behind the C ABI of include/cbs_b200.h).
+
+The function names and argument meaning follow the Rust functions they replace
+(/root/reference/submission/cbs_lib/src/*.rs and the two server stage binaries); each wrapper
+cites the function it mirrors.  All arrays are numpy uint64 in the flat layouts documented in
+include/cbs_b200.h.  There is NO CPU fallback: importing works anywhere, but any compute call
+raises CbsError when the shared library or a B200 is missing.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libcbs_b200.so")
+_lib = None
+
+LWE_SMALL = 769
+LWE_BIG = 2049
+GLWE_WORDS = 3072
+GLEV_WORDS = 21504
+GGSW_WORDS = 64512
+BSK_WORDS = 768 * 9 * 1024
+KSK_WORDS = 8 * 3 * 4 * 256
+AUTO_WORDS = 10 * 2 * 3 * 3 * 1024
+SS_WORDS = 2 * 2 * 3 * 3 * 1024
+K10_9_WORDS = 4 * 16 * 2 * 3072
+K8_1_WORDS = 8 * 4 * 16 * 2 * 3072
+K0_WORDS = 16 * 2 * 3072
+
+
+class CbsError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libcbs_b200.so and the stage executables in-tree for sm_100a (nvcc cross-compiles
+    without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "all"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise CbsError(f"{_LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+        L = ctypes.CDLL(_LIB_PATH)
+        L.cbs_last_error.restype = ctypes.c_char_p
+        L.cbs_version.restype = ctypes.c_char_p
+        L.cbs_ctx_launch_count.restype = ctypes.c_uint64
+        L.cbs_ctx_launch_count.argtypes = [ctypes.c_void_p]
+        for name in ("cbs_keyset_bsk", "cbs_keyset_ksk", "cbs_keyset_auto", "cbs_keyset_ss",
+                     "cbs_keyset_lwe_sk_small", "cbs_keyset_glwe_sk"):
+            getattr(L, name).restype = ctypes.POINTER(ctypes.c_uint64)
+            getattr(L, name).argtypes = [ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise CbsError(f"{what} failed (code {rc}): {lib().cbs_last_error().decode()}")
+
+
+def _u64(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+
+
+def _out(shape):
+    a = np.zeros(shape, dtype=np.uint64)
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+
+
+def _u8(b):
+    a = np.frombuffer(bytes(b), dtype=np.uint8).copy()
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+
+class KeySet:
+    """Host-side evaluation (and optionally secret) keys in the standard domain.
+
+    Mirrors the tuple returned by generate_fhe_keys (src/bin/client_key_generation.rs:20-86) and the
+    files it writes under io/<size>/{public_keys,secret_keys}/."""
+
+    def __init__(self, handle):
+        self._h = ctypes.c_void_p(handle)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.cbs_keyset_free(self._h)
+            self._h = None
+
+    @classmethod
+    def generate(cls, seed):
+        h = ctypes.c_void_p()
+        _check(lib().cbs_keyset_generate(ctypes.c_uint64(seed), ctypes.byref(h)), "cbs_keyset_generate")
+        return cls(h.value)
+
+    @classmethod
+    def load_dir(cls, io_dir, with_secret=False):
+        h = ctypes.c_void_p()
+        _check(lib().cbs_keyset_load_dir(str(io_dir).encode(), int(with_secret), ctypes.byref(h)), "cbs_keyset_load_dir")
+        return cls(h.value)
+
+    @classmethod
+    def from_arrays(cls, bsk, ksk, auto_std, ss, lwe_sk_small=None, glwe_sk=None):
+        h = ctypes.c_void_p()
+        keep = [_u64(x) for x in (bsk, ksk, auto_std, ss)]
+        sk1 = _u64(lwe_sk_small) if lwe_sk_small is not None else (None, None)
+        sk2 = _u64(glwe_sk) if glwe_sk is not None else (None, None)
+        _check(lib().cbs_keyset_from_arrays(keep[0][1], keep[1][1], keep[2][1], keep[3][1], sk1[1], sk2[1],
+                                            ctypes.byref(h)), "cbs_keyset_from_arrays")
+        return cls(h.value)
+
+    def save_dir(self, io_dir, with_secret=False):
+        _check(lib().cbs_keyset_save_dir(self._h, str(io_dir).encode(), int(with_secret)), "cbs_keyset_save_dir")
+
+    def _arr(self, fn, n, shape):
+        p = getattr(lib(), fn)(self._h)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(n,)).reshape(shape).copy()
+
+    @property
+    def bsk(self):
+        return self._arr("cbs_keyset_bsk", BSK_WORDS, (768, 1, 3, 3, 1024))
+
+    @property
+    def ksk(self):
+        return self._arr("cbs_keyset_ksk", KSK_WORDS, (8, 3, 4, 256))
+
+    @property
+    def auto_std(self):
+        return self._arr("cbs_keyset_auto", AUTO_WORDS, (10, 2, 3, 3, 1024))
+
+    @property
+    def ss(self):
+        return self._arr("cbs_keyset_ss", SS_WORDS, (2, 2, 3, 3, 1024))
+
+    @property
+    def lwe_sk_small(self):
+        return self._arr("cbs_keyset_lwe_sk_small", 768, (768,))
+
+    @property
+    def glwe_sk(self):
+        return self._arr("cbs_keyset_glwe_sk", 2048, (2048,))
+
+    # ---- client-side helpers (seeded; the reference's client binaries are unseeded) ----
+    def gen_transciphering_keys(self, aes_key, seed):
+        """gen_transciphering_keys, src/bin/client_encode_encrypt.rs:9-22 -> (k10_9, k8_1, k0)."""
+        k10_9, p1 = _out((4, 16, 2, GLWE_WORDS))
+        k8_1, p2 = _out((8, 4, 16, 2, GLWE_WORDS))
+        k0, p3 = _out((16, 2, GLWE_WORDS))
+        _, pk = _u8(aes_key)
+        _check(lib().cbs_trans_key_generate(self._h, pk, ctypes.c_uint64(seed), p1, p2, p3), "cbs_trans_key_generate")
+        return k10_9, k8_1, k0
+
+    def encrypt_bits_big(self, bits, seed):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        out, po = _out((bits.size, LWE_BIG))
+        _check(lib().cbs_encrypt_bits_big(self._h, bits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), bits.size,
+                                          ctypes.c_uint64(seed), po), "cbs_encrypt_bits_big")
+        return out
+
+    def encrypt_bits_small(self, bits, seed):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        out, po = _out((bits.size, LWE_SMALL))
+        _check(lib().cbs_encrypt_bits_small(self._h, bits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), bits.size,
+                                            ctypes.c_uint64(seed), po), "cbs_encrypt_bits_small")
+        return out
+
+
+def load_trans_key(path):
+    """bincode AllRdKeys (src/data_struct.rs:11-26) -> (k10_9, k8_1, k0)."""
+    k10_9, p1 = _out((4, 16, 2, GLWE_WORDS))
+    k8_1, p2 = _out((8, 4, 16, 2, GLWE_WORDS))
+    k0, p3 = _out((16, 2, GLWE_WORDS))
+    _check(lib().cbs_trans_key_load(str(path).encode(), p1, p2, p3), "cbs_trans_key_load")
+    return k10_9, k8_1, k0
+
+
+def save_trans_key(path, k10_9, k8_1, k0):
+    a, p1 = _u64(k10_9)
+    b, p2 = _u64(k8_1)
+    c, p3 = _u64(k0)
+    _check(lib().cbs_trans_key_save(str(path).encode(), p1, p2, p3), "cbs_trans_key_save")
+
+
+def load_lwe_list(path):
+    data = ctypes.POINTER(ctypes.c_uint64)()
+    count, words = ctypes.c_uint64(), ctypes.c_uint64()
+    _check(lib().cbs_lwe_list_load(str(path).encode(), ctypes.byref(data), ctypes.byref(count), ctypes.byref(words)),
+           "cbs_lwe_list_load")
+    try:
+        return np.ctypeslib.as_array(data, shape=(count.value * words.value,)).reshape(count.value, words.value).copy()
+    finally:
+        lib().cbs_free(data)
+
+
+def save_lwe_list(path, arr):
+    arr = np.ascontiguousarray(arr, dtype=np.uint64)
+    a, p = _u64(arr)
+    _check(lib().cbs_lwe_list_save(str(path).encode(), p, ctypes.c_uint64(arr.shape[0]), ctypes.c_uint64(arr.shape[1])),
+           "cbs_lwe_list_save")
+
+
+class Context:
+    """One B200: Fourier-domain keys + workspaces (cbs_ctx).  Creation uploads the standard-domain
+    keys and converts them on the GPU, replacing server_encrypted_aes_decryption.rs:645-687."""
+
+    def __init__(self, keyset, device=0):
+        h = ctypes.c_void_p()
+        _check(lib().cbs_ctx_create(keyset._h, int(device), ctypes.byref(h)), "cbs_ctx_create")
+        self._h = h
+        self._keyset = keyset
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.cbs_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def launch_count(self):
+        return int(lib().cbs_ctx_launch_count(self._h))
+
+    def set_stream(self, cuda_stream):
+        _check(lib().cbs_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "cbs_ctx_set_stream")
+
+    def synchronize(self):
+        _check(lib().cbs_ctx_synchronize(self._h), "cbs_ctx_synchronize")
+
+    # ---- cbs_lib stage mirrors (host buffers) ----
+    def keyswitch_lwe_ciphertext_by_glwe_keyswitch(self, lwe_big):
+        """cbs_lib/src/fourier_glwe_keyswitch.rs:344 — LWE(2048) -> LWE(768), batched."""
+        a, pi = _u64(np.reshape(lwe_big, (-1, LWE_BIG)))
+        out, po = _out((a.shape[0], LWE_SMALL))
+        _check(lib().cbs_lwe_keyswitch(self._h, pi, po, a.shape[0]), "cbs_lwe_keyswitch")
+        return out
+
+    def blind_rotate(self, lwe_small):
+        """accumulator (ggsw_conv.rs:250-268) + gen_blind_rotate_local_assign (pbs.rs:70)."""
+        a, pi = _u64(np.reshape(lwe_small, (-1, LWE_SMALL)))
+        out, po = _out((a.shape[0], GLWE_WORDS))
+        _check(lib().cbs_blind_rotate(self._h, pi, po, a.shape[0]), "cbs_blind_rotate")
+        return out
+
+    def glev_from_acc(self, acc):
+        """cbs_lib/src/ggsw_conv.rs:302-314."""
+        a, pi = _u64(np.reshape(acc, (-1, GLWE_WORDS)))
+        out, po = _out((a.shape[0], 7, GLWE_WORDS))
+        _check(lib().cbs_glev_from_acc(self._h, pi, po, a.shape[0]), "cbs_glev_from_acc")
+        return out
+
+    def trace_assign(self, glwe):
+        """trace_assign, cbs_lib/src/automorphism.rs:195 (returns the traced copy)."""
+        a = np.array(np.reshape(glwe, (-1, GLWE_WORDS)), dtype=np.uint64, order="C", copy=True)
+        _check(lib().cbs_trace(self._h, a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), a.shape[0]), "cbs_trace")
+        return a
+
+    def lwe_msb_bit_to_glev_by_trace_with_preprocessing(self, lwe_small):
+        """cbs_lib/src/ggsw_conv.rs:231."""
+        a, pi = _u64(np.reshape(lwe_small, (-1, LWE_SMALL)))
+        out, po = _out((a.shape[0], 7, GLWE_WORDS))
+        _check(lib().cbs_lwe_msb_bit_to_glev(self._h, pi, po, a.shape[0]), "cbs_lwe_msb_bit_to_glev")
+        return out
+
+    def switch_scheme(self, glev):
+        """switch_scheme, cbs_lib/src/ggsw_conv.rs:163."""
+        a, pi = _u64(np.reshape(glev, (-1, GLEV_WORDS)))
+        out, po = _out((a.shape[0], GGSW_WORDS))
+        _check(lib().cbs_scheme_switch(self._h, pi, po, a.shape[0]), "cbs_scheme_switch")
+        return out
+
+    def circuit_bootstrap_lwe_ciphertext_by_trace_with_preprocessing(self, lwe_small):
+        """cbs_lib/src/ggsw_conv.rs:409 (GGSW returned in the standard domain)."""
+        a, pi = _u64(np.reshape(lwe_small, (-1, LWE_SMALL)))
+        out, po = _out((a.shape[0], GGSW_WORDS))
+        _check(lib().cbs_circuit_bootstrap(self._h, pi, po, a.shape[0]), "cbs_circuit_bootstrap")
+        return out
+
+    def evaluate_8_to_8_cipher_lut(self, ggsw_bits, luts):
+        """src/bin/server_encrypted_aes_decryption.rs:550.  ggsw_bits [nbytes][8][GGSW], luts
+        [nbytes][nluts][2][GLWE] -> out [nbytes][nluts][8][2049]."""
+        g, pg = _u64(np.reshape(ggsw_bits, (-1, 8, GGSW_WORDS)))
+        nbytes = g.shape[0]
+        l, pl = _u64(np.reshape(luts, (nbytes, -1, 2, GLWE_WORDS)))
+        nluts = l.shape[1]
+        out, po = _out((nbytes, nluts, 8, LWE_BIG))
+        _check(lib().cbs_lut8_eval(self._h, pg, nbytes, pl, nluts, po), "cbs_lut8_eval")
+        return out
+
+    def aes_first_rounds(self, ct, k10_9):
+        """known_rotate_keyed_lut x4 + he_inv_mix_columns_precomp + he_inv_shift_rows
+        (server_encrypted_aes_decryption.rs:89-128)."""
+        c, pc = _u8(ct)
+        nblocks = c.size // 16
+        k, pk = _u64(k10_9)
+        out, po = _out((nblocks, 128, LWE_BIG))
+        _check(lib().cbs_aes_first_rounds(self._h, pc, nblocks, pk, po), "cbs_aes_first_rounds")
+        return out
+
+    def he_inv_mix_columns_and_shift_rows(self, t4):
+        """he_inv_mix_columns_precomp + he_inv_shift_rows (server_encrypted_aes_decryption.rs:195-265);
+        t4 = [4 (x9,x11,x13,x14)][nblocks][128][2049]."""
+        t, pt = _u64(t4)
+        nblocks = t.shape[1]
+        out, po = _out((nblocks, 128, LWE_BIG))
+        _check(lib().cbs_aes_inv_linear(self._h, pt, nblocks, po), "cbs_aes_inv_linear")
+        return out
+
+    def aes_to_lwe_transciphering(self, ct, k10_9, k8_1, k0):
+        """aes_to_lwe_trasnciphering, src/bin/server_encrypted_aes_decryption.rs:28-191, over all
+        16-byte blocks of `ct` -> [nblocks][128][2049] (MSB first inside each byte)."""
+        c, pc = _u8(ct)
+        nblocks = c.size // 16
+        a, p1 = _u64(k10_9)
+        b, p2 = _u64(k8_1)
+        d, p3 = _u64(k0)
+        out, po = _out((nblocks, 128, LWE_BIG))
+        _check(lib().cbs_aes128_transcipher(self._h, pc, nblocks, p1, p2, p3, po), "cbs_aes128_transcipher")
+        return out
+
+    def max_u16(self, lwe_bits):
+        """stage 8, src/bin/server_encrypted_compute.rs:99-359: [nvals*16][2049] -> [16][2049]."""
+        a, pi = _u64(np.reshape(lwe_bits, (-1, LWE_BIG)))
+        nvals = a.shape[0] // 16
+        out, po = _out((16, LWE_BIG))
+        _check(lib().cbs_max_u16(self._h, pi, nvals, po), "cbs_max_u16")
+        return out
+
+    # ---- device-resident API (bench) ----
+    def upload_trans_key(self, k10_9, k8_1, k0):
+        a, p1 = _u64(k10_9)
+        b, p2 = _u64(k8_1)
+        d, p3 = _u64(k0)
+        _check(lib().cbs_trans_key_upload(self._h, p1, p2, p3), "cbs_trans_key_upload")
+
+    def transcipher_dev(self, d_ct_ptr, nblocks, d_out_ptr):
+        _check(lib().cbs_aes128_transcipher_dev(self._h, ctypes.c_void_p(d_ct_ptr), int(nblocks), ctypes.c_void_p(d_out_ptr)),
+               "cbs_aes128_transcipher_dev")
+
+    def circuit_bootstrap_dev(self, d_in_ptr, count):
+        _check(lib().cbs_circuit_bootstrap_dev(self._h, ctypes.c_void_p(d_in_ptr), int(count)), "cbs_circuit_bootstrap_dev")
+
+    def blind_rotate_dev(self, d_in_ptr, d_acc_ptr, count):
+        _check(lib().cbs_blind_rotate_dev(self._h, ctypes.c_void_p(d_in_ptr), ctypes.c_void_p(d_acc_ptr), int(count)),
+               "cbs_blind_rotate_dev")

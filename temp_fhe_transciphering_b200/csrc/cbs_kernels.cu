@@ -1,0 +1,991 @@
+// cbs_kernels.cu — hand-written sm_100a kernels of the circuit-bootstrapping AES transciphering path.
+//
+// Each kernel states the reference routine it replaces (paths relative to
+// /root/reference/submission/).  Work decomposition common to the FFT kernels: a GROUP of 64
+// threads (2 warps) owns one GLWE ciphertext / accumulator; the ciphertext lives in shared memory
+// as u64, polynomials are transformed with the 3-pass radix-8 FP64 FFT of fft512.cuh, Fourier-domain
+// key material is streamed from L2/HBM with coalesced 16-byte loads (512 B per warp instruction) and
+// the pointwise multiply-accumulate, inverse transform and torus rounding never leave registers.
+// Groups synchronise with named barriers (bar.sync id, 64), never with __syncthreads, so the groups
+// of a CTA drift freely and hide each other's shared-memory and barrier latency.
+#include "cbs_kernels.cuh"
+#include "fft512.cuh"
+#include <cstdio>
+
+namespace cbs {
+
+// ------------------------------------------------------------------------------------------------
+// group plumbing
+struct Group {
+    int t;       // thread index inside the group, 0..63
+    int bar;     // named barrier id (1..15)
+    cplx *scr0;  // two 8 KB transpose tiles used alternately: no WAR barrier between transforms
+    cplx *scr1;
+    int flip;
+};
+
+__device__ __forceinline__ void group_sync(int bar) { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
+
+__device__ __forceinline__ void fwd_fft(cplx v[8], Group &g, const Twiddles &tw)
+{
+    cplx *s = g.flip ? g.scr1 : g.scr0;
+    g.flip ^= 1;
+    fwd_p1(v, s, tw, g.t);
+    group_sync(g.bar);
+    fwd_p2(v, s, tw, g.t);
+    group_sync(g.bar);
+    fwd_p3(v, s, g.t);
+}
+
+__device__ __forceinline__ void inv_fft(cplx v[8], Group &g, const Twiddles &tw)
+{
+    cplx *s = g.flip ? g.scr1 : g.scr0;
+    g.flip ^= 1;
+    inv_p3(v, s, g.t);
+    group_sync(g.bar);
+    inv_p2(v, s, tw, g.t);
+    group_sync(g.bar);
+    inv_p1(v, s, tw, g.t);
+}
+
+// coefficient e (0..2047) of the negacyclic extension of p: p[e] for e < N, -p[e-N] otherwise
+__device__ __forceinline__ uint64_t neg_read(const uint64_t *p, int e)
+{
+    uint64_t x = p[e & 1023];
+    return (e & 1024) ? (0ull - x) : x;
+}
+
+__device__ __forceinline__ cplx ldg_cplx(const double *p)
+{
+    double2 d = __ldg(reinterpret_cast<const double2 *>(p));
+    return cplx{d.x, d.y};
+}
+
+// out[c][k3] += v[k3] * key_c[k3*64 + t]   for c < NOUT; key polys are consecutive Fourier polys
+template <int NOUT>
+__device__ __forceinline__ void mul_acc(cplx (&out)[NOUT][8], const cplx v[8], const double *key, int t)
+{
+#pragma unroll
+    for (int c = 0; c < NOUT; c++) {
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++) {
+            cplx w = ldg_cplx(key + (size_t)c * kFourierPolyDoubles + (size_t)(k3 * 64 + t) * 2);
+            cfma(out[c][k3], v[k3], w);
+        }
+    }
+}
+
+// all LEVEL digits of x packed W = BASE_LOG+1 bits each, finest level in the low bits
+template <int BASE_LOG, int LEVEL, typename PackT>
+__device__ __forceinline__ PackT pack_digits(uint64_t x)
+{
+    constexpr int W = BASE_LOG + 1;
+    uint64_t st = decomp_init(x, BASE_LOG, LEVEL);
+    PackT p = 0;
+#pragma unroll
+    for (int tt = 0; tt < LEVEL; tt++) {
+        int32_t d = decomp_next(st, BASE_LOG);
+        p |= (PackT)((uint32_t)d & ((1u << W) - 1u)) << (tt * W);
+    }
+    return p;
+}
+template <int BASE_LOG, typename PackT>
+__device__ __forceinline__ int32_t unpack_digit(PackT p, int tt)
+{
+    constexpr int W = BASE_LOG + 1;
+    uint32_t raw = (uint32_t)(p >> (tt * W)) & ((1u << W) - 1u);
+    return (int32_t)(raw << (32 - W)) >> (32 - W);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: standard -> Fourier conversion (tfhe convert_standard_*_to_fourier; call sites
+// src/bin/server_encrypted_aes_decryption.rs:646-687; split limbs
+// cbs_lib/src/fourier_glwe_keyswitch.rs:188-199)
+constexpr int kConvGroups = 4;
+__global__ void __launch_bounds__(64 * kConvGroups) k_std_to_fourier(const uint64_t *__restrict__ in,
+                                                                      double *__restrict__ out, int npoly, int mode,
+                                                                      int split, const double *__restrict__ twtab)
+{
+    __shared__ cplx scr[kConvGroups][512];
+    Group g;
+    g.t = threadIdx.x & 63;
+    const int gi = threadIdx.x >> 6;
+    g.bar = 1 + gi;
+    g.scr0 = g.scr1 = scr[gi];
+    g.flip = 0;
+    const int poly = blockIdx.x * kConvGroups + gi;
+    if (poly >= npoly) return;
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
+    const uint64_t *p = in + (size_t)poly * 1024;
+    cplx v[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        uint64_t lo = p[g.t + 64 * m], hi = p[g.t + 64 * m + 512];
+        if (mode == 1) {
+            lo = (lo << (64 - split)) >> (64 - split);
+            hi = (hi << (64 - split)) >> (64 - split);
+        } else if (mode == 2) {
+            lo >>= split;
+            hi >>= split;
+        }
+        v[m] = cplx{torus_to_double(lo), torus_to_double(hi)};
+    }
+    fwd_fft(v, g, tw);
+    double *o = out + (size_t)poly * kFourierPolyDoubles;
+#pragma unroll
+    for (int k3 = 0; k3 < 8; k3++) {
+        double2 w = make_double2(v[k3].x * (1.0 / 512.0), v[k3].y * (1.0 / 512.0));
+        *reinterpret_cast<double2 *>(o + (size_t)(k3 * 64 + g.t) * 2) = w;
+    }
+}
+
+void launch_std_to_fourier(const uint64_t *in, double *out, int npoly, int mode, int split, const double *tw,
+                           cudaStream_t s)
+{
+    if (npoly <= 0) return;
+    k_std_to_fourier<<<(npoly + kConvGroups - 1) / kConvGroups, 64 * kConvGroups, 0, s>>>(in, out, npoly, mode, split, tw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 128-point transform for the keyswitch ring N' = 256: batched radix-2 in shared memory,
+// DIF forward (natural -> bit reversed), DIT inverse.  tw128 layout: [128] twist exp(i*pi*j/256),
+// then [64] w = exp(-2*pi*i*j/128).
+constexpr int kKsThreads = 256;
+
+__device__ __forceinline__ void fft128_fwd_batch(cplx *data, int narr, const cplx *w)
+{
+    for (int len = 128; len >= 2; len >>= 1) {
+        const int half = len >> 1, step = 128 / len;
+        for (int id = threadIdx.x; id < narr * 64; id += kKsThreads) {
+            const int arr = id >> 6, b = id & 63;
+            const int blk = b / half, j = b - blk * half;
+            cplx *base = data + arr * 128 + blk * len;
+            cplx u = base[j], x = base[j + half];
+            base[j] = cadd(u, x);
+            base[j + half] = cmul(csub(u, x), w[j * step]);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void fft128_inv_batch(cplx *data, int narr, const cplx *w)
+{
+    for (int len = 2; len <= 128; len <<= 1) {
+        const int half = len >> 1, step = 128 / len;
+        for (int id = threadIdx.x; id < narr * 64; id += kKsThreads) {
+            const int arr = id >> 6, b = id & 63;
+            const int blk = b / half, j = b - blk * half;
+            cplx *base = data + arr * 128 + blk * len;
+            cplx u = base[j], x = cmul_conj(base[j + half], w[j * step]);
+            base[j] = cadd(u, x);
+            base[j + half] = csub(u, x);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kKsThreads) k_ksk_to_fourier(const uint64_t *__restrict__ in,
+                                                                double *__restrict__ out, int npoly,
+                                                                const double *__restrict__ tw128)
+{
+    __shared__ cplx data[128];
+    __shared__ cplx twist[128];
+    __shared__ cplx w[64];
+    const int poly = blockIdx.x;
+    if (poly >= npoly) return;
+    for (int i = threadIdx.x; i < 128; i += kKsThreads) twist[i] = cplx{tw128[2 * i], tw128[2 * i + 1]};
+    for (int i = threadIdx.x; i < 64; i += kKsThreads) w[i] = cplx{tw128[256 + 2 * i], tw128[256 + 2 * i + 1]};
+    __syncthreads();
+    const uint64_t *p = in + (size_t)poly * 256;
+    for (int j = threadIdx.x; j < 128; j += kKsThreads)
+        data[j] = cmul(cplx{torus_to_double(p[j]), torus_to_double(p[j + 128])}, twist[j]);
+    __syncthreads();
+    fft128_fwd_batch(data, 1, w);
+    for (int j = threadIdx.x; j < 128; j += kKsThreads) {
+        out[((size_t)poly * 128 + j) * 2] = data[j].x * (1.0 / 128.0);
+        out[((size_t)poly * 128 + j) * 2 + 1] = data[j].y * (1.0 / 128.0);
+    }
+}
+
+void launch_ksk_to_fourier(const uint64_t *in, double *out, int npoly, const double *tw128, cudaStream_t s)
+{
+    k_ksk_to_fourier<<<npoly, kKsThreads, 0, s>>>(in, out, npoly, tw128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: keyswitch_lwe_ciphertext_by_glwe_keyswitch, cbs_lib/src/fourier_glwe_keyswitch.rs:344-379
+// (convert_lwe_to_glwe_const glwe_conv.rs:12-44 -> keyswitch_glwe_ciphertext :213-342, Vanilla FFT,
+// B = 2^4, l = 3, ring N' = 256 -> sample extract 0).  One CTA per ciphertext; the 24 digit
+// polynomials are transformed together so a whole keyswitch needs 14 CTA barriers.
+constexpr int kKsSmemBytes = (24 * 128 + 128 + 64) * (int)sizeof(cplx);
+
+__global__ void __launch_bounds__(kKsThreads) k_lwe_keyswitch(const uint64_t *__restrict__ in,
+                                                               uint64_t *__restrict__ out, int count,
+                                                               const double *__restrict__ ksk_f,
+                                                               const double *__restrict__ tw128)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *F = reinterpret_cast<cplx *>(smem_raw);  // [24][128]
+    cplx *twist = F + 24 * 128;
+    cplx *w = twist + 128;
+    const int ct = blockIdx.x;
+    if (ct >= count) return;
+    const uint64_t *a = in + (size_t)ct * kLweBig;
+    for (int i = threadIdx.x; i < 128; i += kKsThreads) twist[i] = cplx{tw128[2 * i], tw128[2 * i + 1]};
+    for (int i = threadIdx.x; i < 64; i += kKsThreads) w[i] = cplx{tw128[256 + 2 * i], tw128[256 + 2 * i + 1]};
+    __syncthreads();
+    // digits of the const-embedded input, folded + twisted
+    for (int id = threadIdx.x; id < 8 * 128; id += kKsThreads) {
+        const int i = id >> 7, j = id & 127;
+        // const embed: g[0] = a[0], g[j] = -a[256 - j]
+        uint64_t lo = (j == 0) ? a[i * 256] : (0ull - a[i * 256 + 256 - j]);
+        uint64_t hi = 0ull - a[i * 256 + 128 - j];  // coefficient j + 128 -> -a[256 - (j+128)]
+        uint64_t sl = decomp_init(lo, 4, 3), sh = decomp_init(hi, 4, 3);
+#pragma unroll
+        for (int tt = 0; tt < 3; tt++) {
+            double dl = (double)decomp_next(sl, 4), dh = (double)decomp_next(sh, 4);
+            F[(i * 3 + tt) * 128 + j] = cmul(cplx{dl, dh}, twist[j]);
+        }
+    }
+    __syncthreads();
+    fft128_fwd_batch(F, 24, w);
+    // pointwise multiply-accumulate: 4 output polys x 128 bins
+    cplx acc[2];
+    for (int q = 0; q < 2; q++) {
+        const int id = threadIdx.x + q * kKsThreads;  // 0..511
+        const int c = id >> 7, j = id & 127;
+        cplx s = {0.0, 0.0};
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int tt = 0; tt < 3; tt++) {
+                const int lev = 2 - tt;
+                cplx k = ldg_cplx(ksk_f + ((size_t)((i * 3 + lev) * 4 + c) * 128 + j) * 2);
+                cfma(s, F[(i * 3 + tt) * 128 + j], k);
+            }
+        }
+        acc[q] = s;
+    }
+    __syncthreads();
+    for (int q = 0; q < 2; q++) F[threadIdx.x + q * kKsThreads] = acc[q];  // O[c][j] at F[c*128 + j]
+    __syncthreads();
+    fft128_inv_batch(F, 4, w);
+    // untwist, round to the torus, sample-extract coefficient 0
+    uint64_t *o = out + (size_t)ct * kLweSmall;
+    for (int id = threadIdx.x; id < 4 * 128; id += kKsThreads) {
+        const int c = id >> 7, j = id & 127;
+        cplx z = cmul_conj(F[c * 128 + j], twist[j]);
+        uint64_t lo = torus_from_scaled(z.x), hi = torus_from_scaled(z.y);
+        if (c < 3) {
+            // lwe[c*256 + x] = m[0] for x = 0, -m[256 - x] otherwise
+            if (j == 0) o[c * 256] = lo;
+            else o[c * 256 + 256 - j] = 0ull - lo;
+            o[c * 256 + 128 - j] = 0ull - hi;
+        } else if (j == 0) {
+            o[kLweN] = lo + a[kBigN];
+        }
+    }
+}
+
+void launch_lwe_keyswitch(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int count, cudaStream_t s)
+{
+    if (count <= 0) return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_lwe_keyswitch, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsSmemBytes);
+        attr = true;
+    }
+    k_lwe_keyswitch<<<count, kKsThreads, kKsSmemBytes, s>>>(in, out, count, K.ksk_f, K.tw128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: blind rotation.  Accumulator construction cbs_lib/src/ggsw_conv.rs:250-268 and
+// gen_blind_rotate_local_assign cbs_lib/src/pbs.rs:70-161 (fast_pbs_modulus_switch with
+// LutCountLog(3); polynomial_wrapping_monic_monomial_mul_and_subtract utils.rs:503-568; tfhe
+// add_external_product_assign with B = 2^23, l = 1).
+//
+// One group per LWE ciphertext, kBrGroups groups per CTA, 1 CTA per SM.  Per step:
+//   3 x [rotate-subtract + decompose + forward FFT]  ->  9 pointwise MACs against BSK_i  ->
+//   3 x [inverse FFT + torus rounding + accumulate].
+// BSK_i (73,728 B) is read once per group per step with 16-byte coalesced loads; the groups of a
+// CTA walk the key in near lock-step so all but the first read hit L1/L2.
+constexpr int kBrGroups = 4;
+constexpr int kBrGroupSmem = kGlweWords * 8 + 2 * 512 * 16;  // 24 KB accumulator + 2 x 8 KB tiles
+constexpr int kBrSmemBytes = kBrGroups * kBrGroupSmem;
+
+__device__ __forceinline__ int modswitch_dev(uint64_t x)
+{
+    // ((x >> (64 - log2N - 2 + 3)) + 1) >> 1 << 3   (N = 1024, log_lut_count = 3)
+    uint64_t y = x >> 55;
+    y = (y + 1) >> 1;
+    return (int)(y << 3);
+}
+
+__global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate(const uint64_t *__restrict__ lwe,
+                                                                     uint64_t *__restrict__ acc_out, int count,
+                                                                     const double *__restrict__ bsk_f,
+                                                                     const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int ct = blockIdx.x * kBrGroups + gi;
+    if (ct >= count) return;
+    unsigned char *base = smem_raw + (size_t)gi * kBrGroupSmem;
+    uint64_t *acc = reinterpret_cast<uint64_t *>(base);
+    Group g;
+    g.t = threadIdx.x & 63;
+    g.bar = 1 + gi;
+    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
+    const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+    const int t = g.t;
+
+    // acc = (0, 0, A * X^{-b~}),  A[i] = -+2^(61 - 2*(i%8))  (negative for i < 512)
+    {
+        const int bt = modswitch_dev(a[kLweN]);
+        for (int j = t; j < 1024; j += 64) {
+            acc[j] = 0;
+            acc[1024 + j] = 0;
+            const int e = (j + bt) & 2047;
+            const int i = e & 1023;
+            uint64_t val = 1ull << (61 - 2 * (i & 7));
+            const bool neg = (i < 512) != ((e & 1024) != 0);
+            acc[2048 + j] = neg ? (0ull - val) : val;
+        }
+    }
+    group_sync(g.bar);
+
+    for (int i = 0; i < kLweN; i++) {
+        const int d = modswitch_dev(__ldg(a + i)) & 2047;
+        if (d == 0) continue;  // ct1 == 0: the external product adds exactly zero (pbs.rs:111)
+        const double *bsk_i = bsk_f + (size_t)i * 9 * kFourierPolyDoubles;
+        cplx out[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+        for (int r = 0; r < 3; r++) {
+            const uint64_t *p = acc + r * 1024;
+            cplx v[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int j = t + 64 * m;
+                const int e = (j - d) & 2047;
+                uint64_t xl = neg_read(p, e) - p[j];
+                uint64_t xh = neg_read(p, (e + 512) & 2047) - p[j + 512];
+                uint64_t sl = decomp_init(xl, 23, 1), sh = decomp_init(xh, 23, 1);
+                v[m] = cplx{i32_to_double(decomp_next(sl, 23)), i32_to_double(decomp_next(sh, 23))};
+            }
+            fwd_fft(v, g, tw);
+            mul_acc<3>(out, v, bsk_i + (size_t)r * 3 * kFourierPolyDoubles, t);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft(out[c], g, tw);
+            uint64_t *p = acc + c * 1024;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int j = t + 64 * m;
+                p[j] += torus_from_scaled(out[c][m].x);
+                p[j + 512] += torus_from_scaled(out[c][m].y);
+            }
+        }
+    }
+    group_sync(g.bar);
+    uint64_t *o = acc_out + (size_t)ct * kGlweWords;
+    for (int j = t; j < kGlweWords; j += 64) o[j] = acc[j];
+}
+
+void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc, int count, cudaStream_t s)
+{
+    if (count <= 0) return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
+        attr = true;
+    }
+    k_blind_rotate<<<(count + kBrGroups - 1) / kBrGroups, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f,
+                                                                                               K.tw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a2: cbs_lib/src/ggsw_conv.rs:302-314 — X^-k, + 2^(log_scale-1), sample extract 0,
+// lwe_preprocessing_assign (mod_switch.rs:52-74 == >> 10), convert_lwe_to_glwe_const.
+// extract-then-embed is the identity on the mask, so level k is: mask polys = (acc * X^-k) >> 10,
+// body = [(acc.body[k] + 2^(63-2(k+1))) >> 10, 0, 0, ...].
+__device__ __forceinline__ uint64_t glev_pre_word(const uint64_t *acc, int lvl, int p, int j)
+{
+    if (p < 2) return neg_read(acc + p * 1024, (j + lvl) & 2047) >> 10;
+    if (j != 0) return 0;
+    return (acc[2048 + lvl] + (1ull << (63 - 2 * (lvl + 1)))) >> 10;
+}
+
+__global__ void k_glev_from_acc(const uint64_t *__restrict__ acc, uint64_t *__restrict__ glev, int count)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)count * kGlevWords) return;
+    const int ct = (int)(idx / kGlevWords);
+    const int rem = (int)(idx % kGlevWords);
+    const int lvl = rem / kGlweWords, w = rem % kGlweWords;
+    glev[idx] = glev_pre_word(acc + (size_t)ct * kGlweWords, lvl, w >> 10, w & 1023);
+}
+
+void launch_glev_from_acc(const uint64_t *acc, uint64_t *glev, int count, cudaStream_t s)
+{
+    if (count <= 0) return;
+    const size_t total = (size_t)count * kGlevWords;
+    k_glev_from_acc<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(acc, glev, count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: trace_assign, cbs_lib/src/automorphism.rs:195-233: 10 x [X -> X^kappa (utils.rs:475-490),
+// keyswitch_glwe_ciphertext with Split(41) two-limb FFT (fourier_glwe_keyswitch.rs:213-342), add].
+constexpr int kTrGroups = 3;
+constexpr int kTrGroupSmem = 2 * kGlweWords * 8 + 2 * 512 * 16;  // cur + nxt + 2 tiles = 64 KB
+constexpr int kTrSmemBytes = kTrGroups * kTrGroupSmem;
+__constant__ int c_kappa_inv[10];  // kappa^-1 mod 2048 for kappa = (1024 >> s) + 1
+
+__global__ void __launch_bounds__(64 * kTrGroups, 1) k_trace(const uint64_t *__restrict__ in,
+                                                              uint64_t *__restrict__ out, int count, int from_acc,
+                                                              const double *__restrict__ auto_f,
+                                                              const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int idx = blockIdx.x * kTrGroups + gi;
+    if (idx >= count) return;
+    unsigned char *base = smem_raw + (size_t)gi * kTrGroupSmem;
+    uint64_t *cur = reinterpret_cast<uint64_t *>(base);
+    uint64_t *nxt = cur + kGlweWords;
+    Group g;
+    g.t = threadIdx.x & 63;
+    g.bar = 1 + gi;
+    g.scr0 = reinterpret_cast<cplx *>(base + 2 * kGlweWords * 8);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
+    const int t = g.t;
+
+    if (from_acc) {
+        const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
+        const int lvl = idx % kCbsLevel;
+        for (int w = t; w < kGlweWords; w += 64) cur[w] = glev_pre_word(acc, lvl, w >> 10, w & 1023);
+    } else {
+        const uint64_t *src = in + (size_t)idx * kGlweWords;
+        for (int w = t; w < kGlweWords; w += 64) cur[w] = src[w];
+    }
+    group_sync(g.bar);
+
+#pragma unroll 1
+    for (int s = 0; s < 10; s++) {
+        const int kinv = c_kappa_inv[s];
+        // nxt = cur + (0, 0, body(X^kappa))   (keyswitch output starts as (0, .., 0, body))
+        for (int m = 0; m < 16; m++) {
+            const int j = t + 64 * m;
+            nxt[j] = cur[j];
+            nxt[1024 + j] = cur[1024 + j];
+            nxt[2048 + j] = cur[2048 + j] + neg_read(cur + 2048, (j * kinv) & 2047);
+        }
+#pragma unroll 1
+        for (int sp = 0; sp < 2; sp++) {
+            cplx acc[3][8];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+            for (int i = 0; i < 2; i++) {
+                uint64_t pk[16];
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const int j = t + 64 * m;
+                    pk[2 * m] = pack_digits<13, 3, uint64_t>(neg_read(cur + i * 1024, (j * kinv) & 2047));
+                    pk[2 * m + 1] = pack_digits<13, 3, uint64_t>(neg_read(cur + i * 1024, ((j + 512) * kinv) & 2047));
+                }
+#pragma unroll 1
+                for (int tt = 0; tt < 3; tt++) {
+                    const int lev = 2 - tt;
+                    cplx v[8];
+#pragma unroll
+                    for (int m = 0; m < 8; m++)
+                        v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m], tt)),
+                                    i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m + 1], tt))};
+                    fwd_fft(v, g, tw);
+                    const double *key = auto_f + (size_t)((((s * 2 + i) * 2 + sp) * 3 + lev) * 3) * kFourierPolyDoubles;
+                    mul_acc<3>(acc, v, key, t);
+                }
+            }
+            const int shift = sp ? 41 : 0;  // fourier_glwe_keyswitch.rs:334-339
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                inv_fft(acc[c], g, tw);
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const int j = t + 64 * m;
+                    nxt[c * 1024 + j] += torus_from_scaled(acc[c][m].x) << shift;
+                    nxt[c * 1024 + j + 512] += torus_from_scaled(acc[c][m].y) << shift;
+                }
+            }
+        }
+        group_sync(g.bar);
+        uint64_t *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+    uint64_t *dst = out + (size_t)idx * kGlweWords;
+    for (int w = t; w < kGlweWords; w += 64) dst[w] = cur[w];
+}
+
+void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int count, int from_acc, cudaStream_t s)
+{
+    if (count <= 0) return;
+    static bool init = false;
+    if (!init) {
+        int kinv[10];
+        for (int i = 0; i < 10; i++) {
+            const int kappa = (1024 >> i) + 1;
+            int x = 1;
+            for (int c = 1; c < 2048; c += 2)
+                if ((c * kappa) % 2048 == 1) x = c;
+            kinv[i] = x;
+        }
+        cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
+        cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmemBytes);
+        init = true;
+    }
+    k_trace<<<(count + kTrGroups - 1) / kTrGroups, 64 * kTrGroups, kTrSmemBytes, s>>>(in, out, count, from_acc, K.auto_f,
+                                                                                       K.tw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: switch_scheme cbs_lib/src/ggsw_conv.rs:163-193 (2 external products with the scheme-switching
+// key, B = 2^17, l = 2, per GLEV level) fused with tfhe convert_standard_ggsw_ciphertext_to_fourier
+// (call sites server_encrypted_aes_decryption.rs:430-436): every finished row is rounded to the
+// torus exactly like the reference and immediately forward-transformed from registers.
+constexpr int kSsGroups = 4;
+constexpr int kSsGroupSmem = kGlweWords * 8 + 2 * 512 * 16;  // 40 KB
+constexpr int kSsSmemBytes = kSsGroups * kSsGroupSmem;
+
+__device__ __forceinline__ void emit_row_poly(const uint64_t lo[8], const uint64_t hi[8], uint64_t *std_dst,
+                                              double *f_dst, Group &g, const Twiddles &tw)
+{
+    const int t = g.t;
+    if (std_dst) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            std_dst[t + 64 * m] = lo[m];
+            std_dst[t + 64 * m + 512] = hi[m];
+        }
+    }
+    if (f_dst) {
+        cplx v[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) v[m] = cplx{torus_to_double(lo[m]), torus_to_double(hi[m])};
+        fwd_fft(v, g, tw);
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++)
+            *reinterpret_cast<double2 *>(f_dst + (size_t)(k3 * 64 + t) * 2) =
+                make_double2(v[k3].x * (1.0 / 512.0), v[k3].y * (1.0 / 512.0));
+    }
+}
+
+__global__ void __launch_bounds__(64 * kSsGroups, 1) k_scheme_switch(const uint64_t *__restrict__ glev,
+                                                                      uint64_t *__restrict__ ggsw_std,
+                                                                      double *__restrict__ ggsw_f, int count,
+                                                                      const double *__restrict__ ss_f,
+                                                                      const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int idx = blockIdx.x * kSsGroups + gi;  // (ciphertext, level)
+    if (idx >= count * kCbsLevel) return;
+    unsigned char *base = smem_raw + (size_t)gi * kSsGroupSmem;
+    uint64_t *gl = reinterpret_cast<uint64_t *>(base);
+    Group g;
+    g.t = threadIdx.x & 63;
+    g.bar = 1 + gi;
+    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
+    const int t = g.t;
+    const uint64_t *src = glev + (size_t)idx * kGlweWords;
+    for (int w = t; w < kGlweWords; w += 64) gl[w] = src[w];
+    group_sync(g.bar);
+    // GGSW layout [level][row][poly]; idx = ct*7 + level
+    uint64_t *std_base = ggsw_std ? ggsw_std + (size_t)idx * 3 * kGlweWords : nullptr;
+    double *f_base = ggsw_f ? ggsw_f + (size_t)idx * 9 * kFourierPolyDoubles : nullptr;
+
+#pragma unroll 1
+    for (int i = 0; i < 2; i++) {
+        cplx acc[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+        for (int r = 0; r < 3; r++) {
+            uint64_t pk[16];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                pk[2 * m] = pack_digits<17, 2, uint64_t>(gl[r * 1024 + t + 64 * m]);
+                pk[2 * m + 1] = pack_digits<17, 2, uint64_t>(gl[r * 1024 + t + 64 * m + 512]);
+            }
+#pragma unroll 1
+            for (int tt = 0; tt < 2; tt++) {
+                const int lev = 1 - tt;
+                cplx v[8];
+#pragma unroll
+                for (int m = 0; m < 8; m++)
+                    v[m] = cplx{i32_to_double(unpack_digit<17, uint64_t>(pk[2 * m], tt)),
+                                i32_to_double(unpack_digit<17, uint64_t>(pk[2 * m + 1], tt))};
+                fwd_fft(v, g, tw);
+                const double *key = ss_f + (size_t)(((i * 2 + lev) * 3 + r) * 3) * kFourierPolyDoubles;
+                mul_acc<3>(acc, v, key, t);
+            }
+        }
+#pragma unroll 1
+        for (int c = 0; c < 3; c++) {
+            inv_fft(acc[c], g, tw);
+            uint64_t lo[8], hi[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                lo[m] = torus_from_scaled(acc[c][m].x);
+                hi[m] = torus_from_scaled(acc[c][m].y);
+            }
+            emit_row_poly(lo, hi, std_base ? std_base + (size_t)(i * 3 + c) * 1024 : nullptr,
+                          f_base ? f_base + (size_t)(i * 3 + c) * kFourierPolyDoubles : nullptr, g, tw);
+        }
+    }
+    // row k = the GLEV level itself (ggsw_conv.rs:191)
+#pragma unroll 1
+    for (int c = 0; c < 3; c++) {
+        uint64_t lo[8], hi[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            lo[m] = gl[c * 1024 + t + 64 * m];
+            hi[m] = gl[c * 1024 + t + 64 * m + 512];
+        }
+        emit_row_poly(lo, hi, std_base ? std_base + (size_t)(6 + c) * 1024 : nullptr,
+                      f_base ? f_base + (size_t)(6 + c) * kFourierPolyDoubles : nullptr, g, tw);
+    }
+}
+
+void launch_scheme_switch(const DeviceKeys &K, const uint64_t *glev, uint64_t *ggsw_std, double *ggsw_f, int count,
+                          cudaStream_t s)
+{
+    if (count <= 0) return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_scheme_switch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemBytes);
+        attr = true;
+    }
+    const int groups = count * kCbsLevel;
+    k_scheme_switch<<<(groups + kSsGroups - 1) / kSsGroups, 64 * kSsGroups, kSsSmemBytes, s>>>(glev, ggsw_std, ggsw_f,
+                                                                                                 count, K.ss_f, K.tw);
+}
+
+void launch_ggsw_to_fourier(const DeviceKeys &K, const uint64_t *ggsw_std, double *ggsw_f, int count, cudaStream_t s)
+{
+    launch_std_to_fourier(ggsw_std, ggsw_f, count * kCbsLevel * 9, 0, 0, K.tw, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: evaluate_8_to_8_cipher_lut, src/bin/server_encrypted_aes_decryption.rs:550-588 (== evaluate_8_to_8_lut
+// cbs_lib/src/aes_he.rs:791-832): per accumulator 8 x [acc*X^(-2^i) - acc ; add_external_product_assign
+// with GGSW bit i, B = 2^2, l = 7], then 4 sample extractions at 0, 256, 512, 768.
+constexpr int kLutGroups = 4;
+constexpr int kLutGroupSmem = kGlweWords * 8 + 2 * 512 * 16;  // 40 KB
+constexpr int kLutSmemBytes = kLutGroups * kLutGroupSmem;
+
+// acc += ggsw (x) (src_a - src_b) where the difference is formed per coefficient by `coef`
+template <typename CoefFn>
+__device__ __forceinline__ void cbs_external_product(cplx (&out)[3][8], const double *ggsw, Group &g,
+                                                     const Twiddles &tw, CoefFn coef)
+{
+    const int t = g.t;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+    for (int r = 0; r < 3; r++) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            pk[2 * m] = pack_digits<2, 7, uint32_t>(coef(r, t + 64 * m));
+            pk[2 * m + 1] = pack_digits<2, 7, uint32_t>(coef(r, t + 64 * m + 512));
+        }
+#pragma unroll 1
+        for (int tt = 0; tt < 7; tt++) {
+            const int lev = 6 - tt;
+            cplx v[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                v[m] = cplx{i32_to_double(unpack_digit<2, uint32_t>(pk[2 * m], tt)),
+                            i32_to_double(unpack_digit<2, uint32_t>(pk[2 * m + 1], tt))};
+            fwd_fft(v, g, tw);
+            mul_acc<3>(out, v, ggsw + (size_t)((lev * 3 + r) * 3) * kFourierPolyDoubles, t);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8(const double *__restrict__ ggsw_f,
+                                                              const uint64_t *__restrict__ luts,
+                                                              const int *__restrict__ lut_index,
+                                                              const int *__restrict__ out_index,
+                                                              uint64_t *__restrict__ out, int njobs, int accs_per_byte,
+                                                              const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int job = blockIdx.x * kLutGroups + gi;
+    if (job >= njobs) return;
+    unsigned char *base = smem_raw + (size_t)gi * kLutGroupSmem;
+    uint64_t *acc = reinterpret_cast<uint64_t *>(base);
+    Group g;
+    g.t = threadIdx.x & 63;
+    g.bar = 1 + gi;
+    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
+    const int t = g.t;
+    const uint64_t *src = luts + (size_t)lut_index[job] * kGlweWords;
+    for (int w = t; w < kGlweWords; w += 64) acc[w] = src[w];
+    group_sync(g.bar);
+    const double *bits = ggsw_f + (size_t)(job / accs_per_byte) * 8 * kGgswWords;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        const int d = 1 << i;
+        cplx o[3][8];
+        cbs_external_product(o, bits + (size_t)i * kGgswWords, g, tw, [&](int r, int j) {
+            return neg_read(acc + r * 1024, (j + d) & 2047) - acc[r * 1024 + j];  // acc * X^-d - acc
+        });
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft(o[c], g, tw);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                acc[c * 1024 + t + 64 * m] += torus_from_scaled(o[c][m].x);
+                acc[c * 1024 + t + 64 * m + 512] += torus_from_scaled(o[c][m].y);
+            }
+        }
+    }
+    group_sync(g.bar);
+    // sample extraction at degree 256*q  ->  LWE(2048)
+    for (int q = 0; q < 4; q++) {
+        const int T = 256 * q;
+        uint64_t *o = out + (size_t)(out_index[job] + q) * kLweBig;
+        for (int w = t; w < 2048; w += 64) {
+            const int c = w >> 10, j = w & 1023;
+            const uint64_t *mp = acc + c * 1024;
+            o[w] = (j <= T) ? mp[T - j] : (0ull - mp[1024 + T - j]);
+        }
+        if (t == 0) o[2048] = acc[2048 + T];
+    }
+}
+
+void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts, const int *lut_index,
+                 const int *out_index, uint64_t *out, int njobs, int accs_per_byte, cudaStream_t s)
+{
+    if (njobs <= 0) return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_lut8, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutSmemBytes);
+        attr = true;
+    }
+    k_lut8<<<(njobs + kLutGroups - 1) / kLutGroups, 64 * kLutGroups, kLutSmemBytes, s>>>(ggsw_f, luts, lut_index, out_index,
+                                                                                          out, njobs, accs_per_byte, K.tw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a8: known_rotate_keyed_lut, cbs_lib/src/aes_he.rs:64-93 (rounds 10 + 9: the AES ciphertext byte is
+// public, so the keyed LUT is "rotated" by plain sample extraction at lut_idx*256 + byte).
+// t4 layout [4 mult][nblocks][128][2049]; k10_9 layout [4][16][2][3072]; ct = raw AES ciphertext bytes.
+__global__ void k_known_rotate(const uint8_t *__restrict__ ct, const uint64_t *__restrict__ k10_9,
+                               uint64_t *__restrict__ t4, int nblocks)
+{
+    const int lweid = blockIdx.x;  // (m, blk, i)
+    const int i = lweid % 128, blk = (lweid / 128) % nblocks, m = lweid / (128 * nblocks);
+    const int byte = i >> 3, bit = i & 7;
+    // cleartext inv_shift_rows of the AES ciphertext (server_encrypted_aes_decryption.rs:89-91,590-597)
+    const int row = byte & 3, col = byte >> 2;
+    const int T = (bit & 3) * 256 + ct[blk * 16 + 4 * ((col - row + 4) & 3) + row];
+    const uint64_t *glwe = k10_9 + (size_t)((m * 16 + byte) * 2 + (bit >> 2)) * kGlweWords;
+    uint64_t *o = t4 + (size_t)lweid * kLweBig;
+    for (int w = threadIdx.x; w < 2048; w += blockDim.x) {
+        const int c = w >> 10, j = w & 1023;
+        const uint64_t *mp = glwe + c * 1024;
+        o[w] = (j <= T) ? mp[T - j] : (0ull - mp[1024 + T - j]);
+    }
+    if (threadIdx.x == 0) o[2048] = glwe[2048 + T];
+}
+
+void launch_known_rotate(const uint8_t *ct, const uint64_t *k10_9, uint64_t *t4, int nblocks, cudaStream_t s)
+{
+    if (nblocks <= 0) return;
+    k_known_rotate<<<4 * nblocks * 128, 256, 0, s>>>(ct, k10_9, t4, nblocks);
+}
+
+// a9: he_inv_mix_columns_precomp + he_inv_shift_rows, src/bin/server_encrypted_aes_decryption.rs:195-265,
+// fused into one gather-add (LWE addition = XOR at delta = 2^63).  byte index = 4*col + row.
+__global__ void k_inv_linear(const uint64_t *__restrict__ t4, uint64_t *__restrict__ st, int nblocks)
+{
+    const int lweid = blockIdx.x;  // (blk, byte, bit)
+    const int bit = lweid & 7, byte = (lweid >> 3) & 15, blk = lweid >> 7;
+    const int row = byte & 3, col = byte >> 2;
+    const int scol = (4 - row + col) & 3;  // inv shift rows source column (row 0: identity)
+    const size_t mult = (size_t)nblocks * 128 * kLweBig;
+    auto src = [&](int m, int r) {
+        return t4 + (size_t)m * mult + ((size_t)blk * 128 + (size_t)(4 * scol + (r & 3)) * 8 + bit) * kLweBig;
+    };
+    const uint64_t *p14 = src(3, row), *p11 = src(1, row + 1), *p13 = src(2, row + 2), *p9 = src(0, row + 3);
+    uint64_t *o = st + (size_t)lweid * kLweBig;
+    for (int w = threadIdx.x; w < kLweBig; w += blockDim.x) o[w] = p14[w] + p11[w] + p13[w] + p9[w];
+}
+
+void launch_inv_linear(const uint64_t *t4, uint64_t *st, int nblocks, cudaStream_t s)
+{
+    if (nblocks <= 0) return;
+    k_inv_linear<<<nblocks * 128, 256, 0, s>>>(t4, st, nblocks);
+}
+
+// final reversal of the 8 LWE inside every byte (server_encrypted_aes_decryption.rs:182-189)
+__global__ void k_reverse_bits(const uint64_t *__restrict__ in, uint64_t *__restrict__ out)
+{
+    const int lweid = blockIdx.x;
+    const int srcid = (lweid & ~7) | (7 - (lweid & 7));
+    const uint64_t *p = in + (size_t)srcid * kLweBig;
+    uint64_t *o = out + (size_t)lweid * kLweBig;
+    for (int w = threadIdx.x; w < kLweBig; w += blockDim.x) o[w] = p[w];
+}
+
+void launch_reverse_bits(const uint64_t *in, uint64_t *out, int nblocks, cudaStream_t s)
+{
+    if (nblocks <= 0) return;
+    k_reverse_bits<<<nblocks * 128, 256, 0, s>>>(in, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a10: max_of_two, src/bin/server_encrypted_compute.rs:34-98.  One group per (pair, output bit j):
+//   e <- lwe_a[j] (const-embedded);  for i = 15..0 (LSB -> MSB):
+//     m0 = e + Gb[i] (x) (A - e);  m1 = B + Gb[i] (x) (e - B);  e = m0 + Ga[i] (x) (m1 - m0)
+//   with A = embed(lwe_b[j]), B = embed(lwe_a[j]) (the reference's naming is crossed, :78-79).
+// Differences from the reference, both deliberate: e starts from operand a's bit instead
+// of carrying the previous output bit's e, so output bits are independent (parallel) and a == b
+// yields the right value instead of a stale one.
+constexpr int kMaxGroups = 2;
+constexpr int kMaxGroupSmem = 3 * kGlweWords * 8 + 2 * 512 * 16;  // e, m0, m1 + tiles = 88 KB
+constexpr int kMaxSmemBytes = kMaxGroups * kMaxGroupSmem;
+
+__device__ __forceinline__ uint64_t embed_word(const uint64_t *lwe, int p, int j)
+{
+    // convert_lwe_to_glwe_const, cbs_lib/src/glwe_conv.rs:12-44
+    if (p < 2) return (j == 0) ? lwe[p * 1024] : (0ull - lwe[p * 1024 + 1024 - j]);
+    return (j == 0) ? lwe[2048] : 0ull;
+}
+
+__global__ void __launch_bounds__(64 * kMaxGroups, 1) k_max_ladder(const double *__restrict__ ggsw_f,
+                                                                    const uint64_t *__restrict__ lwe,
+                                                                    const int *__restrict__ a_idx,
+                                                                    const int *__restrict__ b_idx,
+                                                                    uint64_t *__restrict__ out, int npairs,
+                                                                    const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int idx = blockIdx.x * kMaxGroups + gi;  // (pair, j)
+    if (idx >= npairs * 16) return;
+    const int pair = idx >> 4, jbit = idx & 15;
+    unsigned char *base = smem_raw + (size_t)gi * kMaxGroupSmem;
+    uint64_t *e = reinterpret_cast<uint64_t *>(base);
+    uint64_t *m0 = e + kGlweWords, *m1 = m0 + kGlweWords;
+    Group g;
+    g.t = threadIdx.x & 63;
+    g.bar = 1 + gi;
+    g.scr0 = reinterpret_cast<cplx *>(base + 3 * kGlweWords * 8);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
+    const int t = g.t;
+    const int va = a_idx[pair], vb = b_idx[pair];
+    const uint64_t *la = lwe + ((size_t)va * 16 + jbit) * kLweBig;  // operand a, bit j  -> "B"
+    const uint64_t *lb = lwe + ((size_t)vb * 16 + jbit) * kLweBig;  // operand b, bit j  -> "A"
+    for (int w = t; w < kGlweWords; w += 64) e[w] = embed_word(la, w >> 10, w & 1023);
+    group_sync(g.bar);
+    cplx o[3][8];
+#pragma unroll 1
+    for (int i = 15; i >= 0; i--) {
+        const double *Ga = ggsw_f + ((size_t)va * 16 + i) * kGgswWords;
+        const double *Gb = ggsw_f + ((size_t)vb * 16 + i) * kGgswWords;
+        // m0 = e + Gb (x) (A - e)
+        cbs_external_product(o, Gb, g, tw, [&](int r, int j) { return embed_word(lb, r, j) - e[r * 1024 + j]; });
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft(o[c], g, tw);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int j = c * 1024 + t + 64 * m;
+                m0[j] = e[j] + torus_from_scaled(o[c][m].x);
+                m0[j + 512] = e[j + 512] + torus_from_scaled(o[c][m].y);
+            }
+        }
+        // m1 = B + Gb (x) (e - B)
+        cbs_external_product(o, Gb, g, tw, [&](int r, int j) { return e[r * 1024 + j] - embed_word(la, r, j); });
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft(o[c], g, tw);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int j = t + 64 * m;
+                m1[c * 1024 + j] = embed_word(la, c, j) + torus_from_scaled(o[c][m].x);
+                m1[c * 1024 + j + 512] = embed_word(la, c, j + 512) + torus_from_scaled(o[c][m].y);
+            }
+        }
+        // e = m0 + Ga (x) (m1 - m0)   (only own coefficients are touched: no cross-thread hazard)
+        cbs_external_product(o, Ga, g, tw, [&](int r, int j) { return m1[r * 1024 + j] - m0[r * 1024 + j]; });
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft(o[c], g, tw);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int j = c * 1024 + t + 64 * m;
+                e[j] = m0[j] + torus_from_scaled(o[c][m].x);
+                e[j + 512] = m0[j + 512] + torus_from_scaled(o[c][m].y);
+            }
+        }
+    }
+    group_sync(g.bar);
+    // extract_lwe_sample_from_glwe_ciphertext(e, 0)
+    uint64_t *dst = out + (size_t)idx * kLweBig;
+    for (int w = t; w < 2048; w += 64) {
+        const int c = w >> 10, j = w & 1023;
+        dst[w] = (j == 0) ? e[c * 1024] : (0ull - e[c * 1024 + 1024 - j]);
+    }
+    if (t == 0) dst[2048] = e[2048];
+}
+
+void launch_max_ladder(const DeviceKeys &K, const double *ggsw_f, const uint64_t *lwe, const int *a_idx,
+                       const int *b_idx, uint64_t *out, int npairs, cudaStream_t s)
+{
+    if (npairs <= 0) return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_max_ladder, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+        attr = true;
+    }
+    const int groups = npairs * 16;
+    k_max_ladder<<<(groups + kMaxGroups - 1) / kMaxGroups, 64 * kMaxGroups, kMaxSmemBytes, s>>>(ggsw_f, lwe, a_idx, b_idx,
+                                                                                                  out, npairs, K.tw);
+}
+
+}  // namespace cbs

@@ -1,0 +1,28 @@
+// client_encode_encrypt <size> [seed] — seeded stand-in for submission/src/bin/client_encode_encrypt.rs:
+// reads datasets/<s>/aes_key.hex and io/<s>/secret_keys/glwe_sk.bin, writes
+// io/<s>/ciphertexts_upload/trans_key.bin (AllRdKeys, src/data_struct.rs:11-26).
+#include "stage_common.h"
+
+int main(int argc, char **argv)
+{
+    long size;
+    if (!parse_size(argc, argv, &size)) return 1;
+    uint64_t seed = 2;
+    if (argc > 2) seed = strtoull(argv[2], nullptr, 10);
+    else if (const char *e = getenv("CBS_SEED")) seed = strtoull(e, nullptr, 10) + 1;
+    const std::string io_dir = std::string("io/") + size_string(size);
+    const std::string data_dir = std::string("datasets/") + size_string(size);
+    std::vector<uint8_t> key;
+    if (!read_hex_file(data_dir + "/aes_key.hex", key) || key.size() != 16) {
+        fprintf(stderr, "Error: cannot read %s/aes_key.hex\n", data_dir.c_str());
+        return 1;
+    }
+    cbs_keyset *ks = nullptr;
+    STAGE_TRY(cbs_keyset_load_dir(io_dir.c_str(), 1, &ks));
+    std::vector<uint64_t> k10_9(CBS_K10_9_WORDS), k8_1(CBS_K8_1_WORDS), k0(CBS_K0_WORDS);
+    STAGE_TRY(cbs_trans_key_generate(ks, key.data(), seed, k10_9.data(), k8_1.data(), k0.data()));
+    STAGE_TRY(cbs_trans_key_save((io_dir + "/ciphertexts_upload/trans_key.bin").c_str(), k10_9.data(), k8_1.data(), k0.data()));
+    printf("Transciphering keys saved to %s/ciphertexts_upload\n", io_dir.c_str());
+    cbs_keyset_free(ks);
+    return 0;
+}

@@ -1,0 +1,66 @@
+// server_encrypted_aes_decryption <size> — drop-in for the reference stage 7 executable
+// (submission/src/bin/server_encrypted_aes_decryption.rs:599-707): same name, argv, input files
+// (datasets/<s>/db.hex, io/<s>/public_keys/{bsk,ksk,auto_keys,ss_key}.bin,
+// io/<s>/ciphertexts_upload/trans_key.bin) and output (io/<s>/ciphertext_aes_download/result.bin).
+// The reference transciphers only the first 16-byte block of db.hex (:613-617); this binary
+// transciphers every block, sharded contiguously over the visible GPUs (CBS_GPUS limits the count).
+#include "stage_common.h"
+
+#include <algorithm>
+#include <thread>
+
+int main(int argc, char **argv)
+{
+    long size;
+    if (!parse_size(argc, argv, &size)) return 1;
+    const std::string io_dir = std::string("io/") + size_string(size);
+    const std::string data_dir = std::string("datasets/") + size_string(size);
+
+    std::vector<uint8_t> ct;
+    if (!read_hex_file(data_dir + "/db.hex", ct) || ct.size() < 16) {
+        fprintf(stderr, "Error: cannot read %s/db.hex\n", data_dir.c_str());
+        return 1;
+    }
+    const int nblocks = (int)(ct.size() / 16);
+
+    cbs_keyset *ks = nullptr;
+    STAGE_TRY(cbs_keyset_load_dir(io_dir.c_str(), 0, &ks));
+    std::vector<uint64_t> k10_9(CBS_K10_9_WORDS), k8_1(CBS_K8_1_WORDS), k0(CBS_K0_WORDS);
+    STAGE_TRY(cbs_trans_key_load((io_dir + "/ciphertexts_upload/trans_key.bin").c_str(), k10_9.data(), k8_1.data(),
+                                 k0.data()));
+
+    int ngpu = 0;
+    if (cbs_device_count(&ngpu) != CBS_OK || ngpu == 0) {
+        fprintf(stderr, "Error: no CUDA device (this executable has no CPU fallback)\n");
+        return 1;
+    }
+    if (const char *e = getenv("CBS_GPUS")) ngpu = std::max(1, std::min(ngpu, atoi(e)));
+    ngpu = std::min(ngpu, nblocks);
+
+    std::vector<uint64_t> result((size_t)nblocks * 128 * CBS_LWE_BIG_WORDS);
+    std::vector<int> rc(ngpu, 0);
+    std::vector<std::string> err(ngpu);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < ngpu; g++) {
+        workers.emplace_back([&, g]() {
+            const int b0 = (int)((long)nblocks * g / ngpu), b1 = (int)((long)nblocks * (g + 1) / ngpu);
+            cbs_ctx *ctx = nullptr;
+            rc[g] = cbs_ctx_create(ks, g, &ctx);
+            if (rc[g] == CBS_OK)
+                rc[g] = cbs_aes128_transcipher(ctx, ct.data() + (size_t)b0 * 16, b1 - b0, k10_9.data(), k8_1.data(), k0.data(),
+                                               result.data() + (size_t)b0 * 128 * CBS_LWE_BIG_WORDS);
+            if (rc[g] != CBS_OK) err[g] = cbs_last_error();
+            cbs_ctx_destroy(ctx);
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int g = 0; g < ngpu; g++)
+        if (rc[g] != CBS_OK) {
+            fprintf(stderr, "Error: GPU %d: %s\n", g, err[g].c_str());
+            return 1;
+        }
+    STAGE_TRY(cbs_lwe_list_save((io_dir + "/ciphertext_aes_download/result.bin").c_str(), result.data(),
+                                (uint64_t)nblocks * 128, CBS_LWE_BIG_WORDS));
+    cbs_keyset_free(ks);
+    return 0;
+}

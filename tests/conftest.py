@@ -1,0 +1,99 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def cbs():
+    import temp_fhe_transciphering_b200 as m
+    if not os.path.exists(m._LIB_PATH):
+        m.build()
+    return m
+
+
+@pytest.fixture(scope="session")
+def orc():
+    import oracle
+    oracle.lib()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def keyset(cbs):
+    """Seeded client keys (binary secrets + Gaussian noise of AES_TIGHT)."""
+    return cbs.KeySet.generate(20261018)
+
+
+@pytest.fixture(scope="session")
+def orc_keys(orc, keyset):
+    return orc.Keys(keyset.bsk, keyset.ksk, keyset.auto_std, keyset.ss)
+
+
+@pytest.fixture(scope="session")
+def ctx(cbs, keyset):
+    c = cbs.Context(keyset, 0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="session")
+def aes_key():
+    import aes_clear
+    return aes_clear.harness_aes_key(None)
+
+
+@pytest.fixture(scope="session")
+def trans_key(keyset, aes_key):
+    return keyset.gen_transciphering_keys(aes_key, 99)
+
+
+def sdiff(a, b):
+    """signed wrap-around difference of two u64 arrays as float64."""
+    with np.errstate(over="ignore"):
+        return (np.asarray(a, dtype=np.uint64) - np.asarray(b, dtype=np.uint64)).astype(np.int64).astype(np.float64)
+
+
+def log2max(x):
+    return float(np.log2(np.abs(x).max() + 1.0))
+
+
+def glwe_phase(glwe, glwe_sk):
+    """body - sum_c mask_c * S_c  (negacyclic), for GLWE [.., 3, 1024] with binary key [2][1024]."""
+    g = np.asarray(glwe, dtype=np.uint64).reshape(-1, 3, 1024)
+    s = np.asarray(glwe_sk, dtype=np.uint64).reshape(2, 1024)
+    out = g[:, 2].copy()
+    with np.errstate(over="ignore"):
+        for c in range(2):
+            idx = np.nonzero(s[c])[0]
+            for i in idx:
+                rolled = np.roll(g[:, c], i, axis=1)
+                rolled[:, :i] = np.uint64(0) - rolled[:, :i]
+                out -= rolled
+    return out
