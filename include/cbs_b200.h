@@ -161,6 +161,8 @@ int cbs_trans_key_upload(cbs_ctx *ctx, const uint64_t *k10_9, const uint64_t *k8
 int cbs_aes128_transcipher_dev(cbs_ctx *ctx, const uint8_t *d_ct, int nblocks, uint64_t *d_out);
 int cbs_circuit_bootstrap_dev(cbs_ctx *ctx, const uint64_t *d_in_small, int count);  /* GGSW stays in the workspace */
 int cbs_blind_rotate_dev(cbs_ctx *ctx, const uint64_t *d_in_small, uint64_t *d_acc_out, int count);
+/* measured FP64 FMA throughput of the device (roofline denominator of the FFT kernels) */
+int cbs_measure_fp64_tflops(cbs_ctx *ctx, double *tflops);
 /* plain device buffers for callers without their own allocator */
 int cbs_dev_alloc(cbs_ctx *ctx, size_t bytes, void **dptr);
 int cbs_dev_free(cbs_ctx *ctx, void *dptr);

@@ -337,6 +337,11 @@ class Context:
         _check(lib().cbs_max_u16(self._h, pi, nvals, po), "cbs_max_u16")
         return out
 
+    def measure_fp64_tflops(self):
+        v = ctypes.c_double()
+        _check(lib().cbs_measure_fp64_tflops(self._h, ctypes.byref(v)), "cbs_measure_fp64_tflops")
+        return float(v.value)
+
     # ---- device-resident API (bench) ----
     def upload_trans_key(self, k10_9, k8_1, k0):
         a, p1 = _u64(k10_9)

@@ -442,6 +442,35 @@ int cbs_ctx_synchronize(cbs_ctx *ctx)
     return CBS_OK;
 }
 
+int cbs_measure_fp64_tflops(cbs_ctx *ctx, double *tflops)
+{
+    ENTER(ctx);
+    if (!tflops) return CBS_ERR_ARG;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 20000;
+    double *d;
+    TRY(ws_typed(ctx, "fp64_probe", (size_t)blocks * 256, &d));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+        launch_fp64_peak(d, blocks, iters, ctx->stream);
+        CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->launches += 4;
+    *tflops = 2.0 * 16.0 * (double)iters * 256.0 * blocks / (best * 1e-3) * 1e-12;
+    return check_launch("k_fp64_peak");
+}
+
 int cbs_dev_alloc(cbs_ctx *ctx, size_t bytes, void **dptr)
 {
     ENTER(ctx);

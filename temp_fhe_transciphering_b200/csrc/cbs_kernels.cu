@@ -415,11 +415,15 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
 // ------------------------------------------------------------------------------------------------
 // a2: cbs_lib/src/ggsw_conv.rs:302-314 — X^-k, + 2^(log_scale-1), sample extract 0,
 // lwe_preprocessing_assign (mod_switch.rs:52-74 == >> 10), convert_lwe_to_glwe_const.
-// extract-then-embed is the identity on the mask, so level k is: mask polys = (acc * X^-k) >> 10,
-// body = [(acc.body[k] + 2^(63-2(k+1))) >> 10, 0, 0, ...].
+// extract-then-embed only negates coefficients j >= 1 around the logical shift, so level k is:
+//   mask[c][0] = m[0] >> 10,  mask[c][j] = -((-m[j]) >> 10)  with m = acc.mask[c] * X^-k,
+//   body = [(acc.body[k] + 2^(63-2(k+1))) >> 10, 0, 0, ...].
 __device__ __forceinline__ uint64_t glev_pre_word(const uint64_t *acc, int lvl, int p, int j)
 {
-    if (p < 2) return neg_read(acc + p * 1024, (j + lvl) & 2047) >> 10;
+    if (p < 2) {
+        const uint64_t x = neg_read(acc + p * 1024, (j + lvl) & 2047);
+        return (j == 0) ? (x >> 10) : (0ull - ((0ull - x) >> 10));
+    }
     if (j != 0) return 0;
     return (acc[2048 + lvl] + (1ull << (63 - 2 * (lvl + 1)))) >> 10;
 }
@@ -986,6 +990,30 @@ void launch_max_ladder(const DeviceKeys &K, const double *ggsw_f, const uint64_t
     const int groups = npairs * 16;
     k_max_ladder<<<(groups + kMaxGroups - 1) / kMaxGroups, 64 * kMaxGroups, kMaxSmemBytes, s>>>(ggsw_f, lwe, a_idx, b_idx,
                                                                                                   out, npairs, K.tw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA peak probe (roofline denominator: MEASURED_PEAKS.json has no FP64 figure; SURVEY.md 8(d)
+// asks for it to be measured in the same run).  16 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters)
+{
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double m = 1.0000001, c = 1e-7;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) a[i] = fma(a[i], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+void launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s)
+{
+    k_fp64_peak<<<blocks, 256, 0, s>>>(scratch, iters);
 }
 
 }  // namespace cbs

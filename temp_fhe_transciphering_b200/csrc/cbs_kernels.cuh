@@ -77,4 +77,7 @@ void launch_reverse_bits(const uint64_t *in, uint64_t *out, int nblocks, cudaStr
 void launch_max_ladder(const DeviceKeys &K, const double *ggsw_f, const uint64_t *lwe, const int *a_idx,
                        const int *b_idx, uint64_t *out, int npairs, cudaStream_t s);
 
+// FP64 FMA throughput probe: blocks x 256 threads x iters x 16 FMAs
+void launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s);
+
 }  // namespace cbs

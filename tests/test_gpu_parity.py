@@ -27,7 +27,21 @@ def test_lwe_keyswitch_matches_oracle(ctx, orc, orc_keys, keyset):
     assert log2max(sdiff(got, want)) < 30
     ph = ref_io.lwe_phase(got, keyset.lwe_sk_small)
     assert (ref_io.decode_bit(ph) == bits).all()
-    assert log2max(ref_io.bit_error(ph, bits)) < 52
+    # keyswitch noise: 12 decomposed bits of 2048 mask words -> ~2^(64-12-1) * sqrt(2048/2) ~ 2^56.5
+    assert log2max(ref_io.bit_error(ph, bits)) < 58.5
+
+
+def test_blind_rotate_single_step_matches_oracle(ctx, orc, orc_keys):
+    """One non-zero mask element = one external product: the ciphertexts themselves must agree up to
+    FP64 round-off (B = 2^23 digits x 64-bit key words over 3072 terms: ~2^41)."""
+    rng = np.random.default_rng(21)
+    lwe = np.zeros((4, 769), dtype=np.uint64)
+    for i in range(4):
+        lwe[i, 100 * i + 7] = rng.integers(1 << 56, 1 << 63, dtype=np.uint64)
+        lwe[i, 768] = rng.integers(0, 1 << 63, dtype=np.uint64)
+    got = ctx.blind_rotate(lwe)
+    want = orc.blind_rotate(orc_keys, lwe)
+    assert log2max(sdiff(got, want)) < 44, log2max(sdiff(got, want))
 
 
 def test_blind_rotate_matches_oracle(ctx, orc, orc_keys, keyset):
@@ -35,18 +49,22 @@ def test_blind_rotate_matches_oracle(ctx, orc, orc_keys, keyset):
     small = keyset.encrypt_bits_small(bits, 12)
     got = ctx.blind_rotate(small)
     want = orc.blind_rotate(orc_keys, small)
-    d = sdiff(got, want)
-    # two independent FP64 evaluations of 768 external products (B = 2^23): each carries ~2^45 of
-    # round-off, far below the 2^48.5 blind-rotation noise
-    assert log2max(d) < 48.5, log2max(d)
-    assert np.log2(d.std() + 1) < 46.5
-    # decrypt: coefficient j of the accumulator holds -+2^(61-2(j%8)) per the multi-LUT layout
-    ph = glwe_phase(got, keyset.glwe_sk)
+    # After the first of the 768 external products the two FP64 evaluations round a few digits
+    # differently, which re-randomises the masks, so from then on they are two INDEPENDENT samples of
+    # the same noisy result: their phases differ by sqrt(2) x the blind-rotation noise (2^48.5 std,
+    # dominated by the B = 2^23 decomposition rounding), i.e. ~2^49 std / 2^51 max.
+    # Bit-level agreement of the arithmetic is pinned by the single-step test above.
+    pg, pw = glwe_phase(got, keyset.glwe_sk), glwe_phase(want, keyset.glwe_sk)
+    d = sdiff(pg, pw)
+    assert log2max(d) < 52.0, log2max(d)
+    assert np.log2(d.std() + 1) < 49.7, np.log2(d.std() + 1)
+    # decrypt: coefficient lvl of the accumulator holds bit*2^(64-2(lvl+1)) - 2^(63-2(lvl+1))
+    ph = pg
     for i, b in enumerate(bits):
         for lvl in range(7):
             val = int(ph[i, lvl]) + (1 << (63 - 2 * (lvl + 1)))
             val &= (1 << 64) - 1
-            want_val = int(b) << (64 - 2 * (lvl + 1))
+            want_val = (int(b) << (64 - 2 * (lvl + 1))) & ((1 << 64) - 1)
             err = (val - want_val + (1 << 63)) % (1 << 64) - (1 << 63)
             assert abs(err) < 2 ** 52, (i, lvl, np.log2(abs(err) + 1))
 
@@ -104,9 +122,12 @@ def test_circuit_bootstrap_decrypts(ctx, orc, orc_keys, keyset):
                 worst = max(worst, log2max(sdiff(ph[row], want)))
     # CBS GGSW rows max error 2^49.8 .. 2^50.8
     assert worst < 52.5, worst
-    # and the whole pipeline agrees with the oracle far below that noise
-    want = orc.circuit_bootstrap(orc_keys, small[:2])
-    assert log2max(sdiff(ggsw[:2].reshape(2, -1), want)) < 50
+    # and the whole pipeline agrees with the oracle in PHASE (ciphertexts re-randomise, see above)
+    want = orc.circuit_bootstrap(orc_keys, small[:2]).reshape(2, 7, 3, 3072)
+    for i in range(2):
+        for lvl in range(7):
+            d = sdiff(glwe_phase(ggsw[i, lvl].reshape(3, 3072), keyset.glwe_sk), glwe_phase(want[i, lvl], keyset.glwe_sk))
+            assert log2max(d) < 51.5, (i, lvl, log2max(d))
 
 
 def test_lut8_matches_oracle(ctx, orc, orc_keys, keyset, trans_key):
