@@ -11,6 +11,7 @@
 #include "cbs_kernels.cuh"
 #include "fft512.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace cbs {
 
@@ -400,16 +401,191 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate(const uint64
     for (int j = t; j < kGlweWords; j += 64) o[j] = acc[j];
 }
 
+// ---- TMA-staged variant -----------------------------------------------------------------------------
+// The 4 groups of a CTA consume the same BSK tiles (BSK_i row r = 3 Fourier polys = 24,576 B) in the
+// same order, so each tile is fetched ONCE per CTA with a bulk asynchronous copy (cp.async.bulk, the
+// 1-D TMA path: SASS UBLKCP) into a 2-deep shared-memory ring guarded by full/empty mbarriers, while
+// the groups are still busy with the forward FFT that precedes its use.  This removes the exposed
+// L2 latency of 72 dependent 16-byte loads per thread per step (ncu r01: long_scoreboard was the top
+// stall) and cuts L2->SM key traffic 4x.  Thread 0 of group 0 is the producer; every consumer thread
+// releases a tile with one mbarrier arrive after its last read, so no extra group barrier is needed.
+constexpr int kBrTileBytes = 3 * 512 * 16;  // 24,576
+constexpr int kBrRing = 2;
+constexpr int kBrTmaSmemBytes = kBrGroups * kBrGroupSmem + kBrRing * kBrTileBytes + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_tma(const uint64_t *__restrict__ lwe,
+                                                                         uint64_t *__restrict__ acc_out, int count,
+                                                                         const double *__restrict__ bsk_f,
+                                                                         const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int ct = blockIdx.x * kBrGroups + gi;
+    unsigned char *ring = smem_raw + (size_t)kBrGroups * kBrGroupSmem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes);
+    uint64_t *empty = full + kBrRing;
+    const int active_groups = min(kBrGroups, count - blockIdx.x * kBrGroups);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kBrRing; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, 64 * active_groups);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (ct >= count) return;
+    const bool producer = (threadIdx.x == 0);
+    const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
+    constexpr int kTiles = kLweN * 3;
+    if (producer)
+        for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
+
+    unsigned char *base = smem_raw + (size_t)gi * kBrGroupSmem;
+    uint64_t *acc = reinterpret_cast<uint64_t *>(base);
+    Group g;
+    g.t = threadIdx.x & 63;
+    g.bar = 1 + gi;
+    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
+    const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+    const int t = g.t;
+    {
+        const int bt = modswitch_dev(a[kLweN]);
+        for (int j = t; j < 1024; j += 64) {
+            acc[j] = 0;
+            acc[1024 + j] = 0;
+            const int e = (j + bt) & 2047;
+            const int i = e & 1023;
+            uint64_t val = 1ull << (61 - 2 * (i & 7));
+            const bool neg = (i < 512) != ((e & 1024) != 0);
+            acc[2048 + j] = neg ? (0ull - val) : val;
+        }
+    }
+    group_sync(g.bar);
+
+    int tile = 0;
+#pragma unroll 1
+    for (int i = 0; i < kLweN; i++) {
+        const int d = modswitch_dev(__ldg(a + i)) & 2047;
+        const bool skip = (d == 0);  // ct1 == 0: nothing to add, but the tiles are still consumed
+        cplx out[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+        for (int r = 0; r < 3; r++, tile++) {
+            const int buf = tile % kBrRing;
+            const int use = tile / kBrRing;
+            // refill the buffer that tile-1 occupied with tile-1+ring, once every group released it
+            if (producer && tile >= 1 && tile - 1 + kBrRing < kTiles) {
+                const int pb = (tile - 1) % kBrRing, puse = (tile - 1) / kBrRing;
+                mbar_wait(empty + pb, puse & 1);
+                tma_load_tile(ring + pb * kBrTileBytes, bsk_bytes + (size_t)(tile - 1 + kBrRing) * kBrTileBytes, kBrTileBytes,
+                              full + pb);
+            }
+            cplx v[8];
+            if (!skip) {
+                const uint64_t *p = acc + r * 1024;
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const int j = t + 64 * m;
+                    const int e = (j - d) & 2047;
+                    uint64_t xl = neg_read(p, e) - p[j];
+                    uint64_t xh = neg_read(p, (e + 512) & 2047) - p[j + 512];
+                    uint64_t sl = decomp_init(xl, 23, 1), sh = decomp_init(xh, 23, 1);
+                    v[m] = cplx{i32_to_double(decomp_next(sl, 23)), i32_to_double(decomp_next(sh, 23))};
+                }
+                fwd_fft(v, g, tw);
+            }
+            mbar_wait(full + buf, use & 1);
+            if (!skip) {
+                const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes);
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[c * 512 + k3 * 64 + t]);
+            }
+            mbar_arrive(empty + buf);
+        }
+        if (skip) continue;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft(out[c], g, tw);
+            uint64_t *p = acc + c * 1024;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int j = t + 64 * m;
+                p[j] += torus_from_scaled(out[c][m].x);
+                p[j + 512] += torus_from_scaled(out[c][m].y);
+            }
+        }
+    }
+    group_sync(g.bar);
+    uint64_t *o = acc_out + (size_t)ct * kGlweWords;
+    for (int j = t; j < kGlweWords; j += 64) o[j] = acc[j];
+}
+
+static int br_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CBS_BR_VARIANT");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc, int count, cudaStream_t s)
 {
     if (count <= 0) return;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrTmaSmemBytes);
         attr = true;
     }
-    k_blind_rotate<<<(count + kBrGroups - 1) / kBrGroups, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f,
-                                                                                               K.tw);
+    const int grid = (count + kBrGroups - 1) / kBrGroups;
+    if (br_variant() == 0)
+        k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+    else
+        k_blind_rotate_tma<<<grid, 64 * kBrGroups, kBrTmaSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
 }
 
 // ------------------------------------------------------------------------------------------------
