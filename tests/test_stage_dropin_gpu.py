@@ -1,0 +1,49 @@
+"""Drop-in test of the stage executables: the REFERENCE's own prebuilt client binaries (oracle/_ref,
+unmodified) generate the keys and decrypt the results; OUR server_encrypted_aes_decryption and
+server_encrypted_compute run in between, over the same io/ + datasets/ file contract that
+harness/run_submission.py drives."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+BIN = os.path.join(ROOT, "temp_fhe_transciphering_b200", "bin")
+
+
+def _run(exe, cwd, *args):
+    subprocess.run([exe, "0", *args], cwd=cwd, check=True, stdout=subprocess.DEVNULL, timeout=900)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "client_key_generation")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("nvals", [8, 24])
+def test_reference_clients_around_our_servers(tmp_path, nvals):
+    import aes_clear
+    rng = np.random.default_rng(nvals)
+    vals = rng.integers(0, 65536, nvals).tolist()
+    key = aes_clear.harness_aes_key(None)
+    ct = aes_clear.ecb_encrypt(key, aes_clear.pack_u16_be(vals))
+    d = tmp_path
+    os.makedirs(d / "datasets" / "toy")
+    (d / "datasets" / "toy" / "aes_key.hex").write_text(key.hex())
+    (d / "datasets" / "toy" / "db.hex").write_text(ct.hex())
+    _run(os.path.join(REF, "client_key_generation"), d)          # reference, unseeded
+    _run(os.path.join(REF, "client_encode_encrypt"), d)          # reference
+    _run(os.path.join(BIN, "server_encrypted_aes_decryption"), d)  # ours (all blocks, all visible GPUs)
+    _run(os.path.join(BIN, "server_encrypted_compute"), d)         # ours
+    _run(os.path.join(REF, "client_decrypt_decode_aes_decryption"), d)
+    _run(os.path.join(REF, "client_postprocess_aes_decryption"), d)
+    _run(os.path.join(REF, "client_decrypt_decode"), d)
+    _run(os.path.join(REF, "client_postprocess"), d)
+    got = [int(x) for x in (d / "io" / "toy" / "result_aes.txt").read_text().split()]
+    got_max = [int(x) for x in (d / "io" / "toy" / "result.txt").read_text().split()]
+    assert got == vals
+    assert got_max == [max(vals)]
+    # same bytes on disk as the reference writes: LweCiphertextList of 128 x blocks / 16 ciphertexts
+    assert os.path.getsize(d / "io" / "toy" / "ciphertext_aes_download" / "result.bin") == 8 + nvals * 16 * 2049 * 8 + 32
+    assert os.path.getsize(d / "io" / "toy" / "ciphertexts_download" / "result.bin") == 262_312
