@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_tma(const ui
                                                                          const double *__restrict__ bsk_f,
                                                                          const double *__restrict__ twtab)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int gi = threadIdx.x >> 6;
     const int ct = blockIdx.x * kBrGroups + gi;
     unsigned char *ring = smem_raw + (size_t)kBrGroups * kBrGroupSmem;
@@ -562,12 +562,231 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_tma(const ui
     for (int j = t; j < kGlweWords; j += 64) o[j] = acc[j];
 }
 
+// ---- v3: TMA-staged + instruction diet --------------------------------------------------------------
+// ncu r01 (profiles/r01_blind_rotate_ncu_full.csv) showed the FFT core itself sustains 74 % of the FP64
+// peak at this occupancy (tools/bench_fft) while the whole kernel reached 28 %: the time goes to the
+// glue between transforms.  Changes relative to k_blind_rotate_tma:
+//   * accumulator stored as PAIRS (coef[j], coef[j+512]) so the folded FFT input point, its rotated
+//     partner and the read-modify-write of the update are single 128-bit shared accesses;
+//   * l = 1, B = 2^23 digit computed from the high word only (5 integer ops instead of the generic
+//     multi-level decomposer);
+//   * pass-2 twiddles read from a 1 KB shared table (frees 28 registers: no spills, and room to)
+//   * software-pipeline the BSK tile reads against the multiply-accumulate (next column's 8 values are
+//     in flight while the current column's 32 DFMAs issue), with the first column prefetched before the
+//     last forward pass.
+__device__ __forceinline__ int32_t digit_b23_l1(uint64_t x)
+{
+    // tfhe SignedDecomposer(23, 1): closest representable, balanced digit in (-2^22, 2^22]
+    const uint32_t s = (((uint32_t)(x >> 40)) + 1u) >> 1;  // round(x / 2^41) in [0, 2^23]
+    return (int32_t)s - ((s > (1u << 22)) ? (1 << 23) : 0);
+}
+
+struct __align__(16) u64x2 {
+    uint64_t lo, hi;
+};
+
+__device__ __forceinline__ void fwd_p2_s(cplx v[8], cplx *scr, const cplx *t2s, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) v[mp] = scr[slot(k1, tp, mp)];
+    dft8<false>(v);
+    scr[slot(k1, tp, 0)] = v[0];
+#pragma unroll
+    for (int k2 = 1; k2 < 8; k2++) scr[slot(k1, tp, k2)] = cmul(v[k2], t2s[k2 * 8]);
+}
+__device__ __forceinline__ void inv_p2_s(cplx v[8], cplx *scr, const cplx *t2s, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+    v[0] = scr[slot(k1, tp, 0)];
+#pragma unroll
+    for (int k2 = 1; k2 < 8; k2++) v[k2] = cmul_conj(scr[slot(k1, tp, k2)], t2s[k2 * 8]);
+    dft8<true>(v);
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
+}
+
+constexpr int kBr3GroupSmem = kGlweWords * 8 + 2 * 512 * 16;                         // 40 KB
+constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes + 1024 + 64;  // + t2 table + mbarriers
+
+template <bool T2_SMEM, bool PIPE>
+__global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uint64_t *__restrict__ lwe,
+                                                                        uint64_t *__restrict__ acc_out, int count,
+                                                                        const double *__restrict__ bsk_f,
+                                                                        const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int ct = blockIdx.x * kBrGroups + gi;
+    unsigned char *ring = smem_raw + (size_t)kBrGroups * kBr3GroupSmem;
+    cplx *t2tab = reinterpret_cast<cplx *>(ring + kBrRing * kBrTileBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes + 1024);
+    uint64_t *empty = full + kBrRing;
+    const int active_groups = min(kBrGroups, count - blockIdx.x * kBrGroups);
+    if (threadIdx.x < 64) {  // transposed to [k2][t'] so the 8 distinct lanes read 8 consecutive 16 B words
+        const int tp = threadIdx.x >> 3, k2 = threadIdx.x & 7;
+        t2tab[k2 * 8 + tp] = cplx{twtab[(512 + tp * 8 + k2) * 2], twtab[(512 + tp * 8 + k2) * 2 + 1]};
+    }
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kBrRing; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, 64 * active_groups);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (ct >= count) return;
+    const bool producer = (threadIdx.x == 0);
+    const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
+    constexpr int kTiles = kLweN * 3;
+    if (producer)
+        for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
+
+    unsigned char *base = smem_raw + (size_t)gi * kBr3GroupSmem;
+    u64x2 *acc = reinterpret_cast<u64x2 *>(base);  // [3][512] pairs (coef j, coef j + 512)
+    const int t = threadIdx.x & 63;
+    const int bar = 1 + gi;
+    cplx *scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+    cplx *scr1 = scr0 + 512;
+    int flip = 0;
+    const cplx *t2s = t2tab + (t & 7);
+    const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+    {
+        const int bt = modswitch_dev(a[kLweN]);
+        for (int jj = t; jj < 512; jj += 64) {
+            acc[jj] = u64x2{0, 0};
+            acc[512 + jj] = u64x2{0, 0};
+            u64x2 b;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int j = jj + 512 * h;
+                const int e = (j + bt) & 2047;
+                const int i = e & 1023;
+                uint64_t val = 1ull << (61 - 2 * (i & 7));
+                const bool neg = (i < 512) != ((e & 1024) != 0);
+                (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
+            }
+            acc[1024 + jj] = b;
+        }
+    }
+    group_sync(bar);
+
+    // Twiddles struct view for the shared phase functions that still take t1
+    Twiddles tw;
+    load_twiddles(tw, twtab, t);
+
+    int tile = 0;
+#pragma unroll 1
+    for (int i = 0; i < kLweN; i++) {
+        const int d = modswitch_dev(__ldg(a + i)) & 2047;
+        const bool skip = (d == 0);
+        cplx out[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+        for (int r = 0; r < 3; r++, tile++) {
+            const int buf = tile % kBrRing;
+            const int use = tile / kBrRing;
+            if (producer && tile >= 1 && tile - 1 + kBrRing < kTiles) {
+                const int pb = (tile - 1) % kBrRing, puse = (tile - 1) / kBrRing;
+                mbar_wait(empty + pb, puse & 1);
+                tma_load_tile(ring + pb * kBrTileBytes, bsk_bytes + (size_t)(tile - 1 + kBrRing) * kBrTileBytes, kBrTileBytes,
+                              full + pb);
+            }
+            if (!skip) {
+                cplx v[8];
+                const u64x2 *p = acc + r * 512;
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const int jj = t + 64 * m;
+                    const int e0 = (jj - d) & 2047;
+                    const u64x2 src = p[e0 & 511];
+                    const u64x2 own = p[jj];
+                    const int h = e0 >> 9;  // quarter of the 2N-periodic extension
+                    // (rot_lo, rot_hi) = h0:(lo,hi) h1:(hi,-lo) h2:(-lo,-hi) h3:(-hi,lo)
+                    uint64_t rl = (h & 1) ? src.hi : src.lo;
+                    uint64_t rh = (h & 1) ? src.lo : src.hi;
+                    if (h >= 2) rl = 0ull - rl;
+                    if (h == 1 || h == 2) rh = 0ull - rh;
+                    v[m] = cplx{i32_to_double(digit_b23_l1(rl - own.lo)), i32_to_double(digit_b23_l1(rh - own.hi))};
+                }
+                cplx *s = flip ? scr1 : scr0;
+                flip ^= 1;
+                fwd_p1(v, s, tw, t);
+                group_sync(bar);
+                if (T2_SMEM) fwd_p2_s(v, s, t2s, t);
+                else fwd_p2(v, s, tw, t);
+                group_sync(bar);
+                const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
+                if (PIPE) {
+                    mbar_wait(full + buf, use & 1);  // requested a whole FFT ago: normally already complete
+                    cplx kc[8], kn[8];
+#pragma unroll
+                    for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];  // column 0, overlaps the last pass
+                    fwd_p3(v, s, t);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        if (c < 2) {
+#pragma unroll
+                            for (int k3 = 0; k3 < 8; k3++) kn[k3] = key[(c + 1) * 512 + k3 * 64];
+                        }
+#pragma unroll
+                        for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], kc[k3]);
+#pragma unroll
+                        for (int k3 = 0; k3 < 8; k3++) kc[k3] = kn[k3];
+                    }
+                } else {
+                    fwd_p3(v, s, t);
+                    mbar_wait(full + buf, use & 1);
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+#pragma unroll
+                        for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[c * 512 + k3 * 64]);
+                }
+            } else {
+                mbar_wait(full + buf, use & 1);
+            }
+            mbar_arrive(empty + buf);
+        }
+        if (skip) continue;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            cplx *s = flip ? scr1 : scr0;
+            flip ^= 1;
+            inv_p3(out[c], s, t);
+            group_sync(bar);
+            if (T2_SMEM) inv_p2_s(out[c], s, t2s, t);
+            else inv_p2(out[c], s, tw, t);
+            group_sync(bar);
+            inv_p1(out[c], s, tw, t);
+            u64x2 *p = acc + c * 512;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                u64x2 w = p[t + 64 * m];
+                w.lo += torus_from_scaled(out[c][m].x);
+                w.hi += torus_from_scaled(out[c][m].y);
+                p[t + 64 * m] = w;
+            }
+        }
+    }
+    group_sync(bar);
+    uint64_t *o = acc_out + (size_t)ct * kGlweWords;
+    for (int w = t; w < 3 * 512; w += 64) {
+        const u64x2 x = acc[w];
+        const int c = w >> 9, jj = w & 511;
+        o[c * 1024 + jj] = x.lo;
+        o[c * 1024 + jj + 512] = x.hi;
+    }
+}
+
 static int br_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("CBS_BR_VARIANT");
-        v = e ? atoi(e) : 1;
+        v = e ? atoi(e) : 4;
     }
     return v;
 }
@@ -579,13 +798,25 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     if (!attr) {
         cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrTmaSmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         attr = true;
     }
     const int grid = (count + kBrGroups - 1) / kBrGroups;
     if (br_variant() == 0)
         k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-    else
+    else if (br_variant() == 1)
         k_blind_rotate_tma<<<grid, 64 * kBrGroups, kBrTmaSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+    else if (br_variant() == 2)
+        k_blind_rotate_v3<false, false><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+    else if (br_variant() == 3)
+        k_blind_rotate_v3<true, false><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+    else if (br_variant() == 4)
+        k_blind_rotate_v3<false, true><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+    else
+        k_blind_rotate_v3<true, true><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
 }
 
 // ------------------------------------------------------------------------------------------------
