@@ -606,6 +606,36 @@ __device__ __forceinline__ void inv_p2_s(cplx v[8], cplx *scr, const cplx *t2s, 
     for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
 }
 
+// whole transforms with the pass-2 twiddles in shared memory (t2s = table[k2*8 + t'] + (t & 7))
+__device__ __forceinline__ void fwd_fft_s(cplx v[8], Group &g, const Twiddles &tw, const cplx *t2s)
+{
+    cplx *s = g.flip ? g.scr1 : g.scr0;
+    g.flip ^= 1;
+    fwd_p1(v, s, tw, g.t);
+    group_sync(g.bar);
+    fwd_p2_s(v, s, t2s, g.t);
+    group_sync(g.bar);
+    fwd_p3(v, s, g.t);
+}
+__device__ __forceinline__ void inv_fft_s(cplx v[8], Group &g, const Twiddles &tw, const cplx *t2s)
+{
+    cplx *s = g.flip ? g.scr1 : g.scr0;
+    g.flip ^= 1;
+    inv_p3(v, s, g.t);
+    group_sync(g.bar);
+    inv_p2_s(v, s, t2s, g.t);
+    group_sync(g.bar);
+    inv_p1(v, s, tw, g.t);
+}
+// fill a 64-entry shared table with the pass-2 twiddles transposed to [k2][t'] (conflict-free reads)
+__device__ __forceinline__ void fill_t2_table(cplx *t2tab, const double *twtab, int tid)
+{
+    if (tid < 64) {
+        const int tp = tid >> 3, k2 = tid & 7;
+        t2tab[k2 * 8 + tp] = cplx{twtab[(512 + tp * 8 + k2) * 2], twtab[(512 + tp * 8 + k2) * 2 + 1]};
+    }
+}
+
 constexpr int kBr3GroupSmem = kGlweWords * 8 + 2 * 512 * 16;                         // 40 KB
 constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes + 1024 + 64;  // + t2 table + mbarriers
 
@@ -781,6 +811,177 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
     }
 }
 
+// ---- v5: three transforms in flight per group ----------------------------------------------------------
+// tools/bench_fft shows the FFT core alone reaches 74 % of the FP64 peak at 8 warps/SM while the blind
+// rotation sat at 34-42 %: with 2 warps per scheduler every shared-memory round trip, mbarrier wait and
+// dependent FP64 chain is exposed.  v5 raises instruction-level parallelism instead of occupancy: a
+// group transforms the THREE polynomials of the GLWE together (3 x 8 points in registers, three 8 KB
+// transpose tiles), so each barrier interval carries three independent FFT passes; barriers per step
+// drop from 12 to 6 and the multiply-accumulate runs once per step over the whole 72 KB BSK_i, staged by
+// three bulk copies into a 3-slot shared ring one step ahead.  3 groups (6 warps) per CTA.
+constexpr int kB5Groups = 3;
+constexpr int kB5Ring = 3;
+constexpr int kB5GroupSmem = kGlweWords * 8 + 3 * 512 * 16;  // 24 KB accumulator pairs + 3 tiles = 48 KB
+constexpr int kB5SmemBytes = kB5Groups * kB5GroupSmem + kB5Ring * kBrTileBytes + 64;
+
+__global__ void __launch_bounds__(64 * kB5Groups, 1) k_blind_rotate_v5(const uint64_t *__restrict__ lwe,
+                                                                        uint64_t *__restrict__ acc_out, int count,
+                                                                        const double *__restrict__ bsk_f,
+                                                                        const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int ct = blockIdx.x * kB5Groups + gi;
+    unsigned char *ring = smem_raw + (size_t)kB5Groups * kB5GroupSmem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kB5Ring * kBrTileBytes);
+    uint64_t *empty = full + kB5Ring;
+    const int active_groups = min(kB5Groups, count - blockIdx.x * kB5Groups);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kB5Ring; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, 64 * active_groups);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (ct >= count) return;
+    const bool producer = (threadIdx.x == 0);
+    const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
+    if (producer)
+        for (int b = 0; b < 3; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
+
+    unsigned char *base = smem_raw + (size_t)gi * kB5GroupSmem;
+    u64x2 *acc = reinterpret_cast<u64x2 *>(base);
+    const int t = threadIdx.x & 63;
+    const int bar = 1 + gi;
+    cplx *S0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+    cplx *S1 = S0 + 512, *S2 = S1 + 512;
+    Twiddles tw;
+    load_twiddles(tw, twtab, t);
+    const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+    {
+        const int bt = modswitch_dev(a[kLweN]);
+        for (int jj = t; jj < 512; jj += 64) {
+            acc[jj] = u64x2{0, 0};
+            acc[512 + jj] = u64x2{0, 0};
+            u64x2 b;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int j = jj + 512 * h;
+                const int e = (j + bt) & 2047;
+                const int i = e & 1023;
+                uint64_t val = 1ull << (61 - 2 * (i & 7));
+                const bool neg = (i < 512) != ((e & 1024) != 0);
+                (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
+            }
+            acc[1024 + jj] = b;
+        }
+    }
+    group_sync(bar);
+
+    // refill the ring with the three row tiles of step `step` once every group released the previous ones
+    auto produce = [&](int step) {
+        if (step >= kLweN) return;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            mbar_wait(empty + r, (step - 1) & 1);
+            tma_load_tile(ring + r * kBrTileBytes, bsk_bytes + (size_t)(step * 3 + r) * kBrTileBytes, kBrTileBytes, full + r);
+        }
+    };
+
+#pragma unroll 1
+    for (int i = 0; i < kLweN; i++) {
+        const int d = modswitch_dev(__ldg(a + i)) & 2047;
+        if (d == 0) {  // trivial rotation: nothing to add; consume and release the tiles
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                mbar_wait(full + r, i & 1);
+                mbar_arrive(empty + r);
+            }
+            if (producer) produce(i + 1);
+            continue;
+        }
+        cplx v[3][8];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const u64x2 *p = acc + r * 512;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int jj = t + 64 * m;
+                const int e0 = (jj - d) & 2047;
+                const u64x2 src = p[e0 & 511];
+                const u64x2 own = p[jj];
+                const int h = e0 >> 9;
+                uint64_t rl = (h & 1) ? src.hi : src.lo;
+                uint64_t rh = (h & 1) ? src.lo : src.hi;
+                if (h >= 2) rl = 0ull - rl;
+                if (h == 1 || h == 2) rh = 0ull - rh;
+                v[r][m] = cplx{i32_to_double(digit_b23_l1(rl - own.lo)), i32_to_double(digit_b23_l1(rh - own.hi))};
+            }
+        }
+        fwd_p1(v[0], S0, tw, t);
+        fwd_p1(v[1], S1, tw, t);
+        fwd_p1(v[2], S2, tw, t);
+        group_sync(bar);
+        fwd_p2(v[0], S0, tw, t);
+        fwd_p2(v[1], S1, tw, t);
+        fwd_p2(v[2], S2, tw, t);
+        group_sync(bar);
+        fwd_p3(v[0], S0, t);
+        fwd_p3(v[1], S1, t);
+        fwd_p3(v[2], S2, t);
+
+        cplx out[3][8];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            mbar_wait(full + r, i & 1);
+            const cplx *key = reinterpret_cast<const cplx *>(ring + r * kBrTileBytes) + t;
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const cplx w = key[c * 512 + k3 * 64];
+                    if (r == 0) out[c][k3] = cmul(v[0][k3], w);
+                    else cfma(out[c][k3], v[r][k3], w);
+                }
+            }
+            mbar_arrive(empty + r);
+        }
+        group_sync(bar);  // every thread finished reading the tiles in fwd_p3
+        inv_p3(out[0], S0, t);
+        inv_p3(out[1], S1, t);
+        inv_p3(out[2], S2, t);
+        group_sync(bar);
+        if (producer) produce(i + 1);
+        inv_p2(out[0], S0, tw, t);
+        inv_p2(out[1], S1, tw, t);
+        inv_p2(out[2], S2, tw, t);
+        group_sync(bar);
+        inv_p1(out[0], S0, tw, t);
+        inv_p1(out[1], S1, tw, t);
+        inv_p1(out[2], S2, tw, t);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            u64x2 *p = acc + c * 512;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                u64x2 w = p[t + 64 * m];
+                w.lo += torus_from_scaled(out[c][m].x);
+                w.hi += torus_from_scaled(out[c][m].y);
+                p[t + 64 * m] = w;
+            }
+        }
+        group_sync(bar);  // accumulator updated and tiles free before the next step
+    }
+    uint64_t *o = acc_out + (size_t)ct * kGlweWords;
+    for (int w = t; w < 3 * 512; w += 64) {
+        const u64x2 x = acc[w];
+        const int c = w >> 9, jj = w & 511;
+        o[c * 1024 + jj] = x.lo;
+        o[c * 1024 + jj + 512] = x.hi;
+    }
+}
+
 static int br_variant()
 {
     static int v = -1;
@@ -798,6 +999,7 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     if (!attr) {
         cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrTmaSmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, kB5SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
@@ -805,6 +1007,10 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         attr = true;
     }
     const int grid = (count + kBrGroups - 1) / kBrGroups;
+    if (br_variant() == 6) {
+        k_blind_rotate_v5<<<(count + kB5Groups - 1) / kB5Groups, 64 * kB5Groups, kB5SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+        return;
+    }
     if (br_variant() == 0)
         k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
     else if (br_variant() == 1)
@@ -952,6 +1158,177 @@ __global__ void __launch_bounds__(64 * kTrGroups, 1) k_trace(const uint64_t *__r
     for (int w = t; w < kGlweWords; w += 64) dst[w] = cur[w];
 }
 
+// ---- trace v2: both key limbs in one pass, two cooperating 64-thread sub-groups per GLWE ----------------
+// The Split(41) keyswitch needs Sum_F F x K_lo and Sum_F F x K_hi over the same six digit spectra F.
+// Holding both accumulator sets in one thread (192 registers) is impossible, so k_trace ran two
+// passes and recomputed the six forward FFTs (18 FFTs per step).  Here sub-group A accumulates the lo
+// limb and sub-group B the hi limb; A transforms the digits of mask polynomial 0, B those of mask
+// polynomial 1, and each spectrum is handed to the partner through an 8 KB shared tile written and read
+// in the owner's register-slot order (no transpose, conflict-free).  12 FFTs per step, 8 warps per SM
+// (was 18 FFTs at 6 warps), and the second GLWE copy (`nxt`) is gone: all permuted reads of a step
+// happen before its first write.
+constexpr int kTr2Glwe = 2;                                              // GLWEs per CTA (4 sub-groups, 256 threads)
+constexpr int kTr2GlweSmem = kGlweWords * 8 + 2 * 2 * 8192 + 2 * 2 * 8192;  // cur 24 KB + tiles 32 KB + exchange 32 KB
+constexpr int kTr2SmemBytes = kTr2Glwe * kTr2GlweSmem + 1024;  // + pass-2 twiddle table
+
+__device__ __forceinline__ void unit_sync(int bar) { asm volatile("bar.sync %0, 128;" ::"r"(bar) : "memory"); }
+
+// coefficient e (0..2047) of the negacyclic extension, pair layout: A = (coef[q], coef[q+512]), q = e & 511
+__device__ __forceinline__ uint64_t pair_pick(const u64x2 &A, int h)
+{
+    uint64_t x = (h & 1) ? A.hi : A.lo;
+    return (h & 2) ? (0ull - x) : x;
+}
+
+__global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v2(const uint64_t *__restrict__ in,
+                                                                 uint64_t *__restrict__ out, int count, int from_acc,
+                                                                 const double *__restrict__ auto_f,
+                                                                 const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gl = threadIdx.x >> 7;
+    const int sub = (threadIdx.x >> 6) & 1;
+    const int t = threadIdx.x & 63;
+    const int idx = blockIdx.x * kTr2Glwe + gl;
+    cplx *t2tab = reinterpret_cast<cplx *>(smem_raw + (size_t)kTr2Glwe * kTr2GlweSmem);
+    fill_t2_table(t2tab, twtab, threadIdx.x);
+    __syncthreads();
+    if (idx >= count) return;
+    const cplx *t2s = t2tab + (t & 7);
+    unsigned char *base = smem_raw + (size_t)gl * kTr2GlweSmem;
+    u64x2 *cur = reinterpret_cast<u64x2 *>(base);
+    Group g;
+    g.t = t;
+    g.bar = 1 + gl * 2 + sub;
+    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8 + sub * 16384);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    cplx *X = reinterpret_cast<cplx *>(base + kGlweWords * 8 + 32768);  // [buf 2][sub 2][512]
+    const int ubar = 5 + gl;
+    Twiddles tw;
+    load_twiddles(tw, twtab, t);
+
+    // load (pair layout); from_acc fuses ggsw_conv.rs:302-314
+    {
+        const int u = threadIdx.x & 127;
+        if (from_acc) {
+            const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
+            const int lvl = idx % kCbsLevel;
+            for (int w = u; w < 3 * 512; w += 128) {
+                const int p = w >> 9, jj = w & 511;
+                cur[w] = u64x2{glev_pre_word(acc, lvl, p, jj), glev_pre_word(acc, lvl, p, jj + 512)};
+            }
+        } else {
+            const uint64_t *src = in + (size_t)idx * kGlweWords;
+            for (int w = u; w < 3 * 512; w += 128) {
+                const int p = w >> 9, jj = w & 511;
+                cur[w] = u64x2{src[p * 1024 + jj], src[p * 1024 + jj + 512]};
+            }
+        }
+    }
+    unit_sync(ubar);
+
+#pragma unroll 1
+    for (int s = 0; s < 10; s++) {
+        const int kinv = c_kappa_inv[s];
+        // ---- phase 0: every permuted read of this step (X -> X^kappa, utils.rs:475-490) ----
+        uint64_t pk[16];
+        {
+            const u64x2 *p = cur + sub * 512;  // mask polynomial i = sub
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int jj = t + 64 * m;
+                const int e = (jj * kinv) & 2047;
+                const u64x2 A = p[e & 511];
+                const int h = e >> 9;
+                pk[2 * m] = pack_digits<13, 3, uint64_t>(pair_pick(A, h));
+                pk[2 * m + 1] = pack_digits<13, 3, uint64_t>(pair_pick(A, (h + kinv) & 3));
+            }
+        }
+        u64x2 nb[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int jj = t + 64 * (4 * sub + q);
+            const int e = (jj * kinv) & 2047;
+            const u64x2 A = cur[1024 + (e & 511)];
+            const int h = e >> 9;
+            const u64x2 own = cur[1024 + jj];
+            nb[q] = u64x2{own.lo + pair_pick(A, h), own.hi + pair_pick(A, (h + kinv) & 3)};
+        }
+        unit_sync(ubar);
+        // keyswitch output starts as (0, 0, body(X^kappa)) and is added to the input (automorphism.rs:225-229)
+#pragma unroll
+        for (int q = 0; q < 4; q++) cur[1024 + t + 64 * (4 * sub + q)] = nb[q];
+
+        // ---- phase 1: 3 digit levels of the own mask polynomial; accumulate the own limb over both polynomials ----
+        cplx acc[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+        for (int tt = 0; tt < 3; tt++) {
+            const int lev = 2 - tt;
+            cplx v[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m], tt)),
+                            i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m + 1], tt))};
+            fwd_fft_s(v, g, tw, t2s);
+            cplx *Xw = X + ((tt & 1) * 2 + sub) * 512 + t;
+            const cplx *Xr = X + ((tt & 1) * 2 + (1 - sub)) * 512 + t;
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) Xw[k3 * 64] = v[k3];
+            unit_sync(ubar);
+            // key layout [10][in 2][split 2][level 3][col 3]; limb index = sub
+            const double *k_own = auto_f + (size_t)((((s * 2 + sub) * 2 + sub) * 3 + lev) * 3) * kFourierPolyDoubles;
+            const double *k_oth = auto_f + (size_t)((((s * 2 + (1 - sub)) * 2 + sub) * 3 + lev) * 3) * kFourierPolyDoubles;
+            mul_acc<3>(acc, v, k_own, t);
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) {
+                const cplx o = Xr[k3 * 64];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    cfma(acc[c][k3], o, ldg_cplx(k_oth + (size_t)c * kFourierPolyDoubles + (size_t)(k3 * 64 + t) * 2));
+            }
+        }
+        // ---- phase 2: inverse, torus rounding, hi limb << 41 (fourier_glwe_keyswitch.rs:323-341) ----
+        const int shift = sub ? 41 : 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft_s(acc[c], g, tw, t2s);
+            u64x2 *p = cur + c * 512;
+            if (sub == 0) {
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    u64x2 w = p[t + 64 * m];
+                    w.lo += torus_from_scaled(acc[c][m].x);
+                    w.hi += torus_from_scaled(acc[c][m].y);
+                    p[t + 64 * m] = w;
+                }
+            }
+            unit_sync(ubar);  // A's update of column c is complete before B adds its limb
+            if (sub == 1) {
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    u64x2 w = p[t + 64 * m];
+                    w.lo += torus_from_scaled(acc[c][m].x) << shift;
+                    w.hi += torus_from_scaled(acc[c][m].y) << shift;
+                    p[t + 64 * m] = w;
+                }
+            }
+        }
+        unit_sync(ubar);
+    }
+    uint64_t *dst = out + (size_t)idx * kGlweWords;
+    for (int w = threadIdx.x & 127; w < 3 * 512; w += 128) {
+        const u64x2 x = cur[w];
+        const int c = w >> 9, jj = w & 511;
+        dst[c * 1024 + jj] = x.lo;
+        dst[c * 1024 + jj + 512] = x.hi;
+    }
+}
+
 void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int count, int from_acc, cudaStream_t s)
 {
     if (count <= 0) return;
@@ -967,10 +1344,20 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
         }
         cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
         cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmemBytes);
+        cudaFuncSetAttribute(k_trace_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr2SmemBytes);
         init = true;
     }
-    k_trace<<<(count + kTrGroups - 1) / kTrGroups, 64 * kTrGroups, kTrSmemBytes, s>>>(in, out, count, from_acc, K.auto_f,
-                                                                                       K.tw);
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("CBS_TRACE_VARIANT");
+        variant = e ? atoi(e) : 2;
+    }
+    if (variant == 1)
+        k_trace<<<(count + kTrGroups - 1) / kTrGroups, 64 * kTrGroups, kTrSmemBytes, s>>>(in, out, count, from_acc, K.auto_f,
+                                                                                           K.tw);
+    else
+        k_trace_v2<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr2SmemBytes, s>>>(in, out, count, from_acc,
+                                                                                               K.auto_f, K.tw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1061,7 +1448,7 @@ __global__ void __launch_bounds__(64 * kSsGroups, 1) k_scheme_switch(const uint6
                 mul_acc<3>(acc, v, key, t);
             }
         }
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 3; c++) {
             inv_fft(acc[c], g, tw);
             uint64_t lo[8], hi[8];
