@@ -570,10 +570,11 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_tma(const ui
 //     partner and the read-modify-write of the update are single 128-bit shared accesses;
 //   * l = 1, B = 2^23 digit computed from the high word only (5 integer ops instead of the generic
 //     multi-level decomposer);
-//   * pass-2 twiddles read from a 1 KB shared table (frees 28 registers: no spills, and room to)
-//   * software-pipeline the BSK tile reads against the multiply-accumulate (next column's 8 values are
-//     in flight while the current column's 32 DFMAs issue), with the first column prefetched before the
+//   * the BSK tile reads are software-pipelined against the multiply-accumulate (next column's 8 values
+//     are in flight while the current column's 32 DFMAs issue), the first column prefetched before the
 //     last forward pass.
+// (Tried and rejected on B200: pass-2 twiddles in a shared table, 13.3 vs 12.4 ms; three polynomials in
+//  flight per group with 3 groups per CTA, 18.5 ms: occupancy beats per-thread ILP here.)
 __device__ __forceinline__ int32_t digit_b23_l1(uint64_t x)
 {
     // tfhe SignedDecomposer(23, 1): closest representable, balanced digit in (-2^22, 2^22]
@@ -637,9 +638,8 @@ __device__ __forceinline__ void fill_t2_table(cplx *t2tab, const double *twtab, 
 }
 
 constexpr int kBr3GroupSmem = kGlweWords * 8 + 2 * 512 * 16;                         // 40 KB
-constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes + 1024 + 64;  // + t2 table + mbarriers
+constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes + 64;  // + mbarriers
 
-template <bool T2_SMEM, bool PIPE>
 __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uint64_t *__restrict__ lwe,
                                                                         uint64_t *__restrict__ acc_out, int count,
                                                                         const double *__restrict__ bsk_f,
@@ -649,14 +649,9 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
     const int gi = threadIdx.x >> 6;
     const int ct = blockIdx.x * kBrGroups + gi;
     unsigned char *ring = smem_raw + (size_t)kBrGroups * kBr3GroupSmem;
-    cplx *t2tab = reinterpret_cast<cplx *>(ring + kBrRing * kBrTileBytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes + 1024);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes);
     uint64_t *empty = full + kBrRing;
     const int active_groups = min(kBrGroups, count - blockIdx.x * kBrGroups);
-    if (threadIdx.x < 64) {  // transposed to [k2][t'] so the 8 distinct lanes read 8 consecutive 16 B words
-        const int tp = threadIdx.x >> 3, k2 = threadIdx.x & 7;
-        t2tab[k2 * 8 + tp] = cplx{twtab[(512 + tp * 8 + k2) * 2], twtab[(512 + tp * 8 + k2) * 2 + 1]};
-    }
     if (threadIdx.x == 0) {
         for (int b = 0; b < kBrRing; b++) {
             mbar_init(full + b, 1);
@@ -679,7 +674,6 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
     cplx *scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
     cplx *scr1 = scr0 + 512;
     int flip = 0;
-    const cplx *t2s = t2tab + (t & 7);
     const uint64_t *a = lwe + (size_t)ct * kLweSmall;
     {
         const int bt = modswitch_dev(a[kLweN]);
@@ -746,34 +740,24 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                 flip ^= 1;
                 fwd_p1(v, s, tw, t);
                 group_sync(bar);
-                if (T2_SMEM) fwd_p2_s(v, s, t2s, t);
-                else fwd_p2(v, s, tw, t);
+                fwd_p2(v, s, tw, t);
                 group_sync(bar);
                 const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
-                if (PIPE) {
-                    mbar_wait(full + buf, use & 1);  // requested a whole FFT ago: normally already complete
-                    cplx kc[8], kn[8];
+                mbar_wait(full + buf, use & 1);  // requested a whole FFT ago: normally already complete
+                cplx kc[8], kn[8];
 #pragma unroll
-                    for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];  // column 0, overlaps the last pass
-                    fwd_p3(v, s, t);
+                for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];  // column 0, overlaps the last pass
+                fwd_p3(v, s, t);
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        if (c < 2) {
+                for (int c = 0; c < 3; c++) {
+                    if (c < 2) {
 #pragma unroll
-                            for (int k3 = 0; k3 < 8; k3++) kn[k3] = key[(c + 1) * 512 + k3 * 64];
-                        }
-#pragma unroll
-                        for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], kc[k3]);
-#pragma unroll
-                        for (int k3 = 0; k3 < 8; k3++) kc[k3] = kn[k3];
+                        for (int k3 = 0; k3 < 8; k3++) kn[k3] = key[(c + 1) * 512 + k3 * 64];
                     }
-                } else {
-                    fwd_p3(v, s, t);
-                    mbar_wait(full + buf, use & 1);
 #pragma unroll
-                    for (int c = 0; c < 3; c++)
+                    for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], kc[k3]);
 #pragma unroll
-                        for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[c * 512 + k3 * 64]);
+                    for (int k3 = 0; k3 < 8; k3++) kc[k3] = kn[k3];
                 }
             } else {
                 mbar_wait(full + buf, use & 1);
@@ -787,8 +771,7 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
             flip ^= 1;
             inv_p3(out[c], s, t);
             group_sync(bar);
-            if (T2_SMEM) inv_p2_s(out[c], s, t2s, t);
-            else inv_p2(out[c], s, tw, t);
+            inv_p2(out[c], s, tw, t);
             group_sync(bar);
             inv_p1(out[c], s, tw, t);
             u64x2 *p = acc + c * 512;
@@ -811,183 +794,12 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
     }
 }
 
-// ---- v5: three transforms in flight per group ----------------------------------------------------------
-// tools/bench_fft shows the FFT core alone reaches 74 % of the FP64 peak at 8 warps/SM while the blind
-// rotation sat at 34-42 %: with 2 warps per scheduler every shared-memory round trip, mbarrier wait and
-// dependent FP64 chain is exposed.  v5 raises instruction-level parallelism instead of occupancy: a
-// group transforms the THREE polynomials of the GLWE together (3 x 8 points in registers, three 8 KB
-// transpose tiles), so each barrier interval carries three independent FFT passes; barriers per step
-// drop from 12 to 6 and the multiply-accumulate runs once per step over the whole 72 KB BSK_i, staged by
-// three bulk copies into a 3-slot shared ring one step ahead.  3 groups (6 warps) per CTA.
-constexpr int kB5Groups = 3;
-constexpr int kB5Ring = 3;
-constexpr int kB5GroupSmem = kGlweWords * 8 + 3 * 512 * 16;  // 24 KB accumulator pairs + 3 tiles = 48 KB
-constexpr int kB5SmemBytes = kB5Groups * kB5GroupSmem + kB5Ring * kBrTileBytes + 64;
-
-__global__ void __launch_bounds__(64 * kB5Groups, 1) k_blind_rotate_v5(const uint64_t *__restrict__ lwe,
-                                                                        uint64_t *__restrict__ acc_out, int count,
-                                                                        const double *__restrict__ bsk_f,
-                                                                        const double *__restrict__ twtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6;
-    const int ct = blockIdx.x * kB5Groups + gi;
-    unsigned char *ring = smem_raw + (size_t)kB5Groups * kB5GroupSmem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kB5Ring * kBrTileBytes);
-    uint64_t *empty = full + kB5Ring;
-    const int active_groups = min(kB5Groups, count - blockIdx.x * kB5Groups);
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < kB5Ring; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, 64 * active_groups);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (ct >= count) return;
-    const bool producer = (threadIdx.x == 0);
-    const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
-    if (producer)
-        for (int b = 0; b < 3; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
-
-    unsigned char *base = smem_raw + (size_t)gi * kB5GroupSmem;
-    u64x2 *acc = reinterpret_cast<u64x2 *>(base);
-    const int t = threadIdx.x & 63;
-    const int bar = 1 + gi;
-    cplx *S0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
-    cplx *S1 = S0 + 512, *S2 = S1 + 512;
-    Twiddles tw;
-    load_twiddles(tw, twtab, t);
-    const uint64_t *a = lwe + (size_t)ct * kLweSmall;
-    {
-        const int bt = modswitch_dev(a[kLweN]);
-        for (int jj = t; jj < 512; jj += 64) {
-            acc[jj] = u64x2{0, 0};
-            acc[512 + jj] = u64x2{0, 0};
-            u64x2 b;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int j = jj + 512 * h;
-                const int e = (j + bt) & 2047;
-                const int i = e & 1023;
-                uint64_t val = 1ull << (61 - 2 * (i & 7));
-                const bool neg = (i < 512) != ((e & 1024) != 0);
-                (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
-            }
-            acc[1024 + jj] = b;
-        }
-    }
-    group_sync(bar);
-
-    // refill the ring with the three row tiles of step `step` once every group released the previous ones
-    auto produce = [&](int step) {
-        if (step >= kLweN) return;
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            mbar_wait(empty + r, (step - 1) & 1);
-            tma_load_tile(ring + r * kBrTileBytes, bsk_bytes + (size_t)(step * 3 + r) * kBrTileBytes, kBrTileBytes, full + r);
-        }
-    };
-
-#pragma unroll 1
-    for (int i = 0; i < kLweN; i++) {
-        const int d = modswitch_dev(__ldg(a + i)) & 2047;
-        if (d == 0) {  // trivial rotation: nothing to add; consume and release the tiles
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                mbar_wait(full + r, i & 1);
-                mbar_arrive(empty + r);
-            }
-            if (producer) produce(i + 1);
-            continue;
-        }
-        cplx v[3][8];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            const u64x2 *p = acc + r * 512;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int jj = t + 64 * m;
-                const int e0 = (jj - d) & 2047;
-                const u64x2 src = p[e0 & 511];
-                const u64x2 own = p[jj];
-                const int h = e0 >> 9;
-                uint64_t rl = (h & 1) ? src.hi : src.lo;
-                uint64_t rh = (h & 1) ? src.lo : src.hi;
-                if (h >= 2) rl = 0ull - rl;
-                if (h == 1 || h == 2) rh = 0ull - rh;
-                v[r][m] = cplx{i32_to_double(digit_b23_l1(rl - own.lo)), i32_to_double(digit_b23_l1(rh - own.hi))};
-            }
-        }
-        fwd_p1(v[0], S0, tw, t);
-        fwd_p1(v[1], S1, tw, t);
-        fwd_p1(v[2], S2, tw, t);
-        group_sync(bar);
-        fwd_p2(v[0], S0, tw, t);
-        fwd_p2(v[1], S1, tw, t);
-        fwd_p2(v[2], S2, tw, t);
-        group_sync(bar);
-        fwd_p3(v[0], S0, t);
-        fwd_p3(v[1], S1, t);
-        fwd_p3(v[2], S2, t);
-
-        cplx out[3][8];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            mbar_wait(full + r, i & 1);
-            const cplx *key = reinterpret_cast<const cplx *>(ring + r * kBrTileBytes) + t;
-#pragma unroll
-            for (int k3 = 0; k3 < 8; k3++) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const cplx w = key[c * 512 + k3 * 64];
-                    if (r == 0) out[c][k3] = cmul(v[0][k3], w);
-                    else cfma(out[c][k3], v[r][k3], w);
-                }
-            }
-            mbar_arrive(empty + r);
-        }
-        group_sync(bar);  // every thread finished reading the tiles in fwd_p3
-        inv_p3(out[0], S0, t);
-        inv_p3(out[1], S1, t);
-        inv_p3(out[2], S2, t);
-        group_sync(bar);
-        if (producer) produce(i + 1);
-        inv_p2(out[0], S0, tw, t);
-        inv_p2(out[1], S1, tw, t);
-        inv_p2(out[2], S2, tw, t);
-        group_sync(bar);
-        inv_p1(out[0], S0, tw, t);
-        inv_p1(out[1], S1, tw, t);
-        inv_p1(out[2], S2, tw, t);
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            u64x2 *p = acc + c * 512;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                u64x2 w = p[t + 64 * m];
-                w.lo += torus_from_scaled(out[c][m].x);
-                w.hi += torus_from_scaled(out[c][m].y);
-                p[t + 64 * m] = w;
-            }
-        }
-        group_sync(bar);  // accumulator updated and tiles free before the next step
-    }
-    uint64_t *o = acc_out + (size_t)ct * kGlweWords;
-    for (int w = t; w < 3 * 512; w += 64) {
-        const u64x2 x = acc[w];
-        const int c = w >> 9, jj = w & 511;
-        o[c * 1024 + jj] = x.lo;
-        o[c * 1024 + jj + 512] = x.hi;
-    }
-}
-
 static int br_variant()
 {
     static int v = -1;
     if (v < 0) {
-        const char *e = getenv("CBS_BR_VARIANT");
-        v = e ? atoi(e) : 4;
+        const char *e = getenv("CBS_BR_VARIANT");  // 0 = LDG keys, 1 = TMA ring, 2 = TMA ring + v3 (default)
+        v = e ? atoi(e) : 2;
     }
     return v;
 }
@@ -999,30 +811,16 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     if (!attr) {
         cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrTmaSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, kB5SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         attr = true;
     }
     const int grid = (count + kBrGroups - 1) / kBrGroups;
-    if (br_variant() == 6) {
-        k_blind_rotate_v5<<<(count + kB5Groups - 1) / kB5Groups, 64 * kB5Groups, kB5SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-        return;
-    }
     if (br_variant() == 0)
         k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
     else if (br_variant() == 1)
         k_blind_rotate_tma<<<grid, 64 * kBrGroups, kBrTmaSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-    else if (br_variant() == 2)
-        k_blind_rotate_v3<false, false><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-    else if (br_variant() == 3)
-        k_blind_rotate_v3<true, false><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-    else if (br_variant() == 4)
-        k_blind_rotate_v3<false, true><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
     else
-        k_blind_rotate_v3<true, true><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+        k_blind_rotate_v3<<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
 }
 
 // ------------------------------------------------------------------------------------------------
