@@ -52,6 +52,9 @@ extern "C" {
 #define CBS_K10_9_WORDS     (4u * 16u * 2u * 3072u)
 #define CBS_K8_1_WORDS      (8u * 4u * 16u * 2u * 3072u)
 #define CBS_K0_WORDS        (16u * 2u * 3072u)
+#define CBS_KF_FIRST_WORDS  (3u * 16u * 2u * 3072u)
+#define CBS_KF_MID_WORDS    (8u * 3u * 16u * 2u * 3072u)
+#define CBS_KF_LAST_WORDS   (16u * 2u * 3072u)
 
 typedef struct cbs_keyset cbs_keyset; /* host-side key material, standard domain */
 typedef struct cbs_ctx cbs_ctx;       /* one GPU: Fourier-domain keys + workspaces */
@@ -92,6 +95,16 @@ int cbs_trans_key_save(const char *path, const uint64_t *k10_9, const uint64_t *
  * rounds 10/9 encrypted LUTs, rounds 8..1 and 0 trivial LUTs, for ECB block decryption. */
 int cbs_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *k10_9,
                            uint64_t *k8_1, uint64_t *k0);
+/* Forward-direction transciphering key for CTR mode (the harness uses CTR for sizes 1/2,
+ * harness/aes_keygen_and_encrypt.py:45-55, which the reference does not implement).  Keyed S-boxes as
+ * cbs_lib/src/aes_ref.rs:334-380: kf_first [3 (x1,x2,x3)][16][2] encrypted GLWE LUTs of
+ * m*S(x ^ rk0), kf_mid [8 (rounds 2..9)][3][16][2] trivial LUTs of m*S(x ^ rk_{r-1}), kf_last [16][2]
+ * trivial LUTs of S(x ^ rk9) ^ rk10 (key byte of the post-ShiftRows position).  Same bincode shape as
+ * AllRdKeys with 3-tuples. */
+int cbs_fwd_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *kf_first,
+                               uint64_t *kf_mid, uint64_t *kf_last);
+int cbs_fwd_trans_key_load(const char *path, uint64_t *kf_first, uint64_t *kf_mid, uint64_t *kf_last);
+int cbs_fwd_trans_key_save(const char *path, const uint64_t *kf_first, const uint64_t *kf_mid, const uint64_t *kf_last);
 /* LweCiphertextList<Vec<u64>> result.bin */
 int cbs_lwe_list_load(const char *path, uint64_t **data /* malloc'd, free with cbs_free */, uint64_t *count,
                       uint64_t *lwe_words);
@@ -149,6 +162,11 @@ int cbs_aes_inv_linear(cbs_ctx *ctx, const uint64_t *t4, int nblocks, uint64_t *
  * (the exact payload of ciphertext_aes_download/result.bin). */
 int cbs_aes128_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const uint64_t *k10_9, const uint64_t *k8_1,
                            const uint64_t *k0, uint64_t *out);
+/* CTR-mode transciphering (forward AES on the public counter blocks IV+i, 128-bit big-endian counter as
+ * pyaes.Counter; he_sub_bytes_8_to_24 / he_shift_rows / he_mix_columns_precomp, cbs_lib/src/aes_he.rs:285-474),
+ * then XOR with the public AES-CTR ciphertext bits.  out as cbs_aes128_transcipher. */
+int cbs_aes128_ctr_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const uint8_t iv[16], const uint64_t *kf_first,
+                               const uint64_t *kf_mid, const uint64_t *kf_last, uint64_t *out);
 /* stage 8, src/bin/server_encrypted_compute.rs:99-359: encrypted max of nvals 16-bit values
  * (in[nvals][16] big LWE, MSB first) -> out[16] big LWE.  The reference accepts exactly 8 values
  * (sequential fold); any nvals >= 1 is reduced as a balanced tree here. */
@@ -159,6 +177,9 @@ int cbs_max_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out);
  * Used by bench.py's `value` leg and by callers that keep state on the GPU. */
 int cbs_trans_key_upload(cbs_ctx *ctx, const uint64_t *k10_9, const uint64_t *k8_1, const uint64_t *k0);
 int cbs_aes128_transcipher_dev(cbs_ctx *ctx, const uint8_t *d_ct, int nblocks, uint64_t *d_out);
+int cbs_fwd_trans_key_upload(cbs_ctx *ctx, const uint64_t *kf_first, const uint64_t *kf_mid, const uint64_t *kf_last);
+/* d_ctr = the nblocks counter blocks (16 bytes each), d_ct = the AES-CTR ciphertext bytes */
+int cbs_aes128_ctr_transcipher_dev(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int nblocks, uint64_t *d_out);
 int cbs_circuit_bootstrap_dev(cbs_ctx *ctx, const uint64_t *d_in_small, int count);  /* GGSW stays in the workspace */
 int cbs_blind_rotate_dev(cbs_ctx *ctx, const uint64_t *d_in_small, uint64_t *d_acc_out, int count);
 /* measured FP64 FMA throughput of the device (roofline denominator of the FFT kernels) */

@@ -684,6 +684,112 @@ void orc_aes128_transcipher(const orc_keys *K, const uint8_t *ct, int nblocks, c
     free(ks);
 }
 
+/* ---- forward direction (CTR mode) ---- */
+
+/* he_shift_rows, cbs_lib/src/aes_he.rs:348-366 */
+void orc_shift_rows(uint64_t *st)
+{
+    uint64_t *buf = malloc(sizeof(uint64_t) * 128 * LWE_W);
+    memcpy(buf, st, sizeof(uint64_t) * 128 * LWE_W);
+    for (int row = 1; row < 4; row++)
+        for (int col = 0; col < 4; col++)
+            memcpy(state_byte(st, row, col), state_byte_c(buf, row, (row + col) % 4), sizeof(uint64_t) * 8 * LWE_W);
+    free(buf);
+}
+
+/* he_mix_columns_precomp, cbs_lib/src/aes_he.rs:441-474 (st holds the x1 list on entry) */
+void orc_mix_columns_precomp(uint64_t *st, const uint64_t *t2, const uint64_t *t3)
+{
+    uint64_t *buf = malloc(sizeof(uint64_t) * 128 * LWE_W);
+    memcpy(buf, st, sizeof(uint64_t) * 128 * LWE_W);
+    for (int row = 0; row < 4; row++) {
+        for (int col = 0; col < 4; col++) {
+            uint64_t *d = state_byte(st, row, col);
+            const uint64_t *a = state_byte_c(t2, row, col);
+            const uint64_t *b = state_byte_c(t3, (row + 1) % 4, col);
+            const uint64_t *c = state_byte_c(buf, (row + 2) % 4, col);
+            const uint64_t *e = state_byte_c(buf, (row + 3) % 4, col);
+            for (int j = 0; j < 8 * LWE_W; j++) d[j] = a[j] + b[j] + c[j] + e[j];
+        }
+    }
+    free(buf);
+}
+
+/* AES-128-CTR transciphering: forward AES of the public counter blocks with keyed S-box LUTs
+ * (he_sub_bytes_8_to_24_by_patched_wwlp_cbs aes_he.rs:285, keyed tables aes_ref.rs:334-380), then XOR
+ * with the public ciphertext bits.  The reference has no CTR path; this is the composition of its
+ * forward-direction building blocks that the harness sizes 1/2 require
+ * (harness/aes_keygen_and_encrypt.py:45-55, pyaes.Counter = 128-bit big-endian, +1 per block).
+ * kf_first [3 (x1,x2,x3)][16][2][3072], kf_mid [8 (rounds 2..9)][3][16][2][3072], kf_last [16][2][3072]. */
+void orc_aes128_ctr_transcipher(const orc_keys *K, const uint8_t *ct, int nblocks, const uint8_t *iv,
+                                const uint64_t *kf_first, const uint64_t *kf_mid, const uint64_t *kf_last, uint64_t *out)
+{
+    const size_t ST = (size_t)128 * LWE_W;
+    const size_t MULT = (size_t)16 * 2 * ORC_GLWE_WORDS;
+    uint64_t *st = out;
+    uint64_t *t = malloc(sizeof(uint64_t) * 3 * ST * nblocks);
+    uint64_t *ks = malloc(sizeof(uint64_t) * (size_t)128 * (ORC_LWE_N + 1) * nblocks);
+    uint8_t cur[16];
+    memcpy(cur, iv, 16);
+    for (int blk = 0; blk < nblocks; blk++) {
+        uint64_t *tb = t + (size_t)blk * 3 * ST;
+        for (int m = 0; m < 3; m++) {
+            orc_known_rotate(cur, kf_first + (size_t)m * MULT, tb + (size_t)m * ST);
+            orc_shift_rows(tb + (size_t)m * ST);
+        }
+        memcpy(st + blk * ST, tb, sizeof(uint64_t) * ST);
+        orc_mix_columns_precomp(st + blk * ST, tb + ST, tb + 2 * ST);
+        for (int i = 15; i >= 0; i--)
+            if (++cur[i] != 0) break;
+    }
+    for (int round = 2; round <= 10; round++) {
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long i = 0; i < (long)nblocks * 128; i++)
+            orc_lwe_keyswitch(K, st + (size_t)i * LWE_W, ks + (size_t)i * (ORC_LWE_N + 1));
+#pragma omp parallel for schedule(dynamic, 1)
+        for (long job = 0; job < (long)nblocks * 16; job++) {
+            int blk = (int)(job / 16), byte = (int)(job % 16);
+            const uint64_t *in = ks + ((size_t)blk * 128 + 8 * byte) * (ORC_LWE_N + 1);
+            if (round <= 9) {
+                const uint64_t *luts[3];
+                uint64_t *outs[3];
+                for (int m = 0; m < 3; m++) {
+                    luts[m] = kf_mid + (((size_t)(round - 2) * 3 + m) * 16 + byte) * 2 * ORC_GLWE_WORDS;
+                    outs[m] = t + (size_t)blk * 3 * ST + (size_t)m * ST + (size_t)8 * byte * LWE_W;
+                }
+                sbox_byte(K, in, 3, luts, outs);
+            } else {
+                const uint64_t *luts[1] = {kf_last + (size_t)byte * 2 * ORC_GLWE_WORDS};
+                uint64_t *outs[1] = {st + blk * ST + (size_t)8 * byte * LWE_W};
+                sbox_byte(K, in, 1, luts, outs);
+            }
+        }
+        for (int blk = 0; blk < nblocks; blk++) {
+            if (round <= 9) {
+                uint64_t *tb = t + (size_t)blk * 3 * ST;
+                for (int m = 0; m < 3; m++) orc_shift_rows(tb + (size_t)m * ST);
+                memcpy(st + blk * ST, tb, sizeof(uint64_t) * ST);
+                orc_mix_columns_precomp(st + blk * ST, tb + ST, tb + 2 * ST);
+            } else {
+                orc_shift_rows(st + blk * ST);
+            }
+        }
+    }
+    /* keystream xor public ciphertext bit (bit b of byte at LWE index 8*byte + b), then MSB-first */
+    uint64_t tmp[LWE_W];
+    for (long byte = 0; byte < (long)nblocks * 16; byte++) {
+        uint64_t *b = st + (size_t)8 * byte * LWE_W;
+        for (int i = 0; i < 8; i++) b[(size_t)i * LWE_W + ORC_BIG_N] += (uint64_t)((ct[byte] >> i) & 1) << 63;
+        for (int i = 0; i < 4; i++) {
+            memcpy(tmp, b + (size_t)i * LWE_W, sizeof(tmp));
+            memcpy(b + (size_t)i * LWE_W, b + (size_t)(7 - i) * LWE_W, sizeof(tmp));
+            memcpy(b + (size_t)(7 - i) * LWE_W, tmp, sizeof(tmp));
+        }
+    }
+    free(t);
+    free(ks);
+}
+
 /* tfhe cmux_assign(ct0, ct1, ggsw): ct1 -= ct0; ct0 += ggsw (x) ct1 */
 static void cmux(uint64_t *ct0, uint64_t *ct1, const double *ggsw_f)
 {

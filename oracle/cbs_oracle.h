@@ -125,6 +125,12 @@ void orc_aes128_transcipher(const orc_keys *K, const uint8_t *ct, int nblocks,
                             const uint64_t *k10_9, const uint64_t *k8_1, const uint64_t *k0,
                             uint64_t *out);
 
+/* forward direction / CTR mode: he_shift_rows aes_he.rs:348, he_mix_columns_precomp :441 */
+void orc_shift_rows(uint64_t *st);
+void orc_mix_columns_precomp(uint64_t *st /* x1 in, result out */, const uint64_t *t2, const uint64_t *t3);
+void orc_aes128_ctr_transcipher(const orc_keys *K, const uint8_t *ct, int nblocks, const uint8_t *iv,
+                                const uint64_t *kf_first, const uint64_t *kf_mid, const uint64_t *kf_last, uint64_t *out);
+
 /* a10: max_of_two (server_encrypted_compute.rs:34-98).  ggsw std-domain, 16 each, MSB first.
  * reset_e = 0 reproduces the reference (glwe_e carried across output bits). */
 void orc_max_of_two(const uint64_t *ggsw_a, const uint64_t *ggsw_b,

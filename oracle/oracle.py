@@ -159,6 +159,16 @@ def aes128_transcipher(keys, ct_bytes, k10_9, k8_1, k0):
     return out
 
 
+def aes128_ctr_transcipher(keys, ct_bytes, iv, kf_first, kf_mid, kf_last):
+    ct = np.frombuffer(bytes(ct_bytes), dtype=np.uint8).copy()
+    ivb = np.frombuffer(bytes(iv), dtype=np.uint8).copy()
+    nblocks = ct.size // 16
+    out = np.zeros((nblocks, 128, BIG + 1), dtype=np.uint64)
+    lib().orc_aes128_ctr_transcipher(keys._k, ct.ctypes.data_as(_u8p), ctypes.c_int(nblocks), ivb.ctypes.data_as(_u8p),
+                                     _u(_c(kf_first)), _u(_c(kf_mid)), _u(_c(kf_last)), _u(out))
+    return out
+
+
 def max_of_two(ggsw_a, ggsw_b, lwe_a, lwe_b, reset_e=False):
     out = np.zeros((16, BIG + 1), dtype=np.uint64)
     lib().orc_max_of_two(_u(_c(ggsw_a)), _u(_c(ggsw_b)), _u(_c(lwe_a)), _u(_c(lwe_b)), _u(out), ctypes.c_int(int(reset_e)))

@@ -29,6 +29,9 @@ SS_WORDS = 2 * 2 * 3 * 3 * 1024
 K10_9_WORDS = 4 * 16 * 2 * 3072
 K8_1_WORDS = 8 * 4 * 16 * 2 * 3072
 K0_WORDS = 16 * 2 * 3072
+KF_FIRST_WORDS = 3 * 16 * 2 * 3072
+KF_MID_WORDS = 8 * 3 * 16 * 2 * 3072
+KF_LAST_WORDS = 16 * 2 * 3072
 
 
 class CbsError(RuntimeError):
@@ -161,6 +164,16 @@ class KeySet:
         _check(lib().cbs_trans_key_generate(self._h, pk, ctypes.c_uint64(seed), p1, p2, p3), "cbs_trans_key_generate")
         return k10_9, k8_1, k0
 
+    def gen_forward_transciphering_keys(self, aes_key, seed):
+        """Forward-direction keyed-S-box LUTs for CTR mode (keyed tables cbs_lib/src/aes_ref.rs:334-380)
+        -> (kf_first[3][16][2], kf_mid[8][3][16][2], kf_last[16][2]) GLWE."""
+        a, p1 = _out((3, 16, 2, GLWE_WORDS))
+        b, p2 = _out((8, 3, 16, 2, GLWE_WORDS))
+        c, p3 = _out((16, 2, GLWE_WORDS))
+        _, pk = _u8(aes_key)
+        _check(lib().cbs_fwd_trans_key_generate(self._h, pk, ctypes.c_uint64(seed), p1, p2, p3), "cbs_fwd_trans_key_generate")
+        return a, b, c
+
     def encrypt_bits_big(self, bits, seed):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)
         out, po = _out((bits.size, LWE_BIG))
@@ -190,6 +203,21 @@ def save_trans_key(path, k10_9, k8_1, k0):
     b, p2 = _u64(k8_1)
     c, p3 = _u64(k0)
     _check(lib().cbs_trans_key_save(str(path).encode(), p1, p2, p3), "cbs_trans_key_save")
+
+
+def load_fwd_trans_key(path):
+    a, p1 = _out((3, 16, 2, GLWE_WORDS))
+    b, p2 = _out((8, 3, 16, 2, GLWE_WORDS))
+    c, p3 = _out((16, 2, GLWE_WORDS))
+    _check(lib().cbs_fwd_trans_key_load(str(path).encode(), p1, p2, p3), "cbs_fwd_trans_key_load")
+    return a, b, c
+
+
+def save_fwd_trans_key(path, kf_first, kf_mid, kf_last):
+    a, p1 = _u64(kf_first)
+    b, p2 = _u64(kf_mid)
+    c, p3 = _u64(kf_last)
+    _check(lib().cbs_fwd_trans_key_save(str(path).encode(), p1, p2, p3), "cbs_fwd_trans_key_save")
 
 
 def load_lwe_list(path):
@@ -327,6 +355,20 @@ class Context:
         d, p3 = _u64(k0)
         out, po = _out((nblocks, 128, LWE_BIG))
         _check(lib().cbs_aes128_transcipher(self._h, pc, nblocks, p1, p2, p3, po), "cbs_aes128_transcipher")
+        return out
+
+    def aes_ctr_to_lwe_transciphering(self, ct, iv, kf_first, kf_mid, kf_last):
+        """CTR-mode transciphering: forward AES of the public counter blocks (he_sub_bytes_8_to_24,
+        he_shift_rows, he_mix_columns_precomp; cbs_lib/src/aes_he.rs:285-474) xor the public ciphertext
+        -> [nblocks][128][2049] plaintext bits, MSB first inside each byte."""
+        c, pc = _u8(ct)
+        nblocks = c.size // 16
+        ivb, pi = _u8(iv)
+        a, p1 = _u64(kf_first)
+        b, p2 = _u64(kf_mid)
+        d, p3 = _u64(kf_last)
+        out, po = _out((nblocks, 128, LWE_BIG))
+        _check(lib().cbs_aes128_ctr_transcipher(self._h, pc, nblocks, pi, p1, p2, p3, po), "cbs_aes128_ctr_transcipher")
         return out
 
     def max_u16(self, lwe_bits):

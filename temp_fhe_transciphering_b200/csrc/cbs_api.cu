@@ -39,6 +39,9 @@ struct cbs_ctx {
     std::vector<void *> key_allocs;
     uint64_t *d_k10_9 = nullptr, *d_k8_1 = nullptr, *d_k0 = nullptr;
     bool have_trans_key = false;
+    uint64_t *d_kf_first = nullptr, *d_kf_mid = nullptr, *d_kf_last = nullptr;
+    bool have_fwd_key = false;
+    int jobs24_nblocks = -1;
     std::map<std::string, DevBuf> ws;
     // cached LUT job tables, keyed by block count
     int jobs_nblocks = -1;
@@ -225,7 +228,7 @@ int dev_transcipher_chunk(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d
     TRY(ws_typed(ctx, "ggsw_f", (size_t)B * kGgswWords, &d_ggsw_f));
     TRY(ensure_job_tables(ctx, nb, &lut32, &out32, &lut8, &out8));
     // rounds 10 + 9 (server_encrypted_aes_decryption.rs:89-128)
-    launch_known_rotate(d_ct, ctx->d_k10_9, d_t4, nb, ctx->stream);
+    launch_known_rotate(d_ct, ctx->d_k10_9, d_t4, nb, 4, 1, ctx->stream);
     launch_inv_linear(d_t4, d_st, nb, ctx->stream);
     ctx->launches += 2;
     TRY(check_launch("first rounds"));
@@ -246,6 +249,71 @@ int dev_transcipher_chunk(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d
     launch_reverse_bits(d_st, d_out, nb, ctx->stream);
     ctx->launches += 2;
     return check_launch("last round");
+}
+
+// CTR mode: forward AES of the public counter blocks (aes_he.rs:285-474), one chunk of nb blocks
+int dev_ctr_chunk(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int nb, uint64_t *d_out)
+{
+    const int B = nb * 128;
+    uint64_t *d_t3, *d_st, *d_ks;
+    double *d_ggsw_f;
+    int *lut24, *out24, *lut8, *out8, *dummy_a, *dummy_b;
+    TRY(ws_typed(ctx, "t4", (size_t)4 * B * kLweBig, &d_t3));
+    TRY(ws_typed(ctx, "st", (size_t)B * kLweBig, &d_st));
+    TRY(ws_typed(ctx, "ks", (size_t)B * kLweSmall, &d_ks));
+    TRY(ws_typed(ctx, "ggsw_f", (size_t)B * kGgswWords, &d_ggsw_f));
+    TRY(ensure_job_tables(ctx, nb, &dummy_a, &dummy_b, &lut8, &out8));
+    const int j24 = nb * 16 * 6;
+    TRY(ws_typed(ctx, "job_lut24", (size_t)j24, &lut24));
+    TRY(ws_typed(ctx, "job_out24", (size_t)j24, &out24));
+    if (ctx->jobs24_nblocks != nb) {
+        std::vector<int> l(j24), o(j24);
+        for (int blk = 0; blk < nb; blk++)
+            for (int byte = 0; byte < 16; byte++)
+                for (int m = 0; m < 3; m++)
+                    for (int a = 0; a < 2; a++) {
+                        const int job = (blk * 16 + byte) * 6 + m * 2 + a;
+                        l[job] = (m * 16 + byte) * 2 + a;
+                        o[job] = (m * nb + blk) * 128 + byte * 8 + 4 * a;
+                    }
+        CUDA_TRY(cudaMemcpyAsync(lut24, l.data(), sizeof(int) * j24, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(out24, o.data(), sizeof(int) * j24, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->jobs24_nblocks = nb;
+    }
+    // round 1: the counter block is public -> keyed LUTs are "rotated" by sample extraction
+    launch_known_rotate(d_ctr, ctx->d_kf_first, d_t3, nb, 3, 0, ctx->stream);
+    launch_fwd_linear(d_t3, d_st, nb, ctx->stream);
+    ctx->launches += 2;
+    TRY(check_launch("ctr round 1"));
+    for (int round = 2; round <= 9; round++) {
+        TRY(dev_keyswitch(ctx, d_st, d_ks, B));
+        TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
+        const uint64_t *luts = ctx->d_kf_mid + (size_t)(round - 2) * 3 * 16 * 2 * kGlweWords;
+        launch_lut8(ctx->K, d_ggsw_f, luts, lut24, out24, d_t3, j24, 6, ctx->stream);
+        launch_fwd_linear(d_t3, d_st, nb, ctx->stream);
+        ctx->launches += 2;
+        TRY(check_launch("ctr round"));
+    }
+    TRY(dev_keyswitch(ctx, d_st, d_ks, B));
+    TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
+    launch_lut8(ctx->K, d_ggsw_f, ctx->d_kf_last, lut8, out8, d_st, nb * 16 * 2, 2, ctx->stream);
+    launch_ctr_finish(d_st, d_ct, d_out, nb, ctx->stream);
+    ctx->launches += 2;
+    return check_launch("ctr last round");
+}
+
+int dev_ctr(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int nblocks, uint64_t *d_out)
+{
+    if (!ctx->have_fwd_key) {
+        set_error("forward transciphering key not uploaded (cbs_fwd_trans_key_upload)");
+        return CBS_ERR_ARG;
+    }
+    for (int b0 = 0; b0 < nblocks; b0 += ctx->chunk_blocks) {
+        const int nb = std::min(ctx->chunk_blocks, nblocks - b0);
+        TRY(dev_ctr_chunk(ctx, d_ctr + (size_t)b0 * 16, d_ct + (size_t)b0 * 16, nb, d_out + (size_t)b0 * 128 * kLweBig));
+    }
+    return CBS_OK;
 }
 
 int dev_transcipher(cbs_ctx *ctx, const uint8_t *d_ct, int nblocks, uint64_t *d_out)
@@ -413,6 +481,9 @@ void cbs_ctx_destroy(cbs_ctx *ctx)
     if (ctx->d_k10_9) cudaFree(ctx->d_k10_9);
     if (ctx->d_k8_1) cudaFree(ctx->d_k8_1);
     if (ctx->d_k0) cudaFree(ctx->d_k0);
+    if (ctx->d_kf_first) cudaFree(ctx->d_kf_first);
+    if (ctx->d_kf_mid) cudaFree(ctx->d_kf_mid);
+    if (ctx->d_kf_last) cudaFree(ctx->d_kf_last);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -658,7 +729,7 @@ int cbs_aes_first_rounds(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const uin
     TRY(ws_typed(ctx, "st", (size_t)nblocks * 128 * kLweBig, &d_st));
     TRY(upload(ctx, d_ct, ct, (size_t)nblocks * 16));
     TRY(upload(ctx, d_k, k10_9, (size_t)CBS_K10_9_WORDS * 8));
-    launch_known_rotate(d_ct, d_k, d_t4, nblocks, ctx->stream);
+    launch_known_rotate(d_ct, d_k, d_t4, nblocks, 4, 1, ctx->stream);
     launch_inv_linear(d_t4, d_st, nblocks, ctx->stream);
     ctx->launches += 2;
     TRY(check_launch("first rounds"));
@@ -717,6 +788,59 @@ int cbs_aes128_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const u
     TRY(ws_typed(ctx, "io_result", (size_t)nblocks * 128 * kLweBig, &d_out));
     TRY(upload(ctx, d_ct, ct, (size_t)nblocks * 16));
     TRY(dev_transcipher(ctx, d_ct, nblocks, d_out));
+    return download(ctx, out, d_out, (size_t)nblocks * 128 * kLweBig * 8);
+}
+
+int cbs_fwd_trans_key_upload(cbs_ctx *ctx, const uint64_t *kf_first, const uint64_t *kf_mid, const uint64_t *kf_last)
+{
+    ENTER(ctx);
+    if (!kf_first || !kf_mid || !kf_last) return set_error("cbs_fwd_trans_key_upload: null argument"), CBS_ERR_ARG;
+    if (!ctx->d_kf_first) {
+        CUDA_TRY(cudaMalloc(&ctx->d_kf_first, (size_t)CBS_KF_FIRST_WORDS * 8));
+        CUDA_TRY(cudaMalloc(&ctx->d_kf_mid, (size_t)CBS_KF_MID_WORDS * 8));
+        CUDA_TRY(cudaMalloc(&ctx->d_kf_last, (size_t)CBS_KF_LAST_WORDS * 8));
+    }
+    TRY(upload(ctx, ctx->d_kf_first, kf_first, (size_t)CBS_KF_FIRST_WORDS * 8));
+    TRY(upload(ctx, ctx->d_kf_mid, kf_mid, (size_t)CBS_KF_MID_WORDS * 8));
+    TRY(upload(ctx, ctx->d_kf_last, kf_last, (size_t)CBS_KF_LAST_WORDS * 8));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->have_fwd_key = true;
+    return CBS_OK;
+}
+
+int cbs_aes128_ctr_transcipher_dev(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int nblocks, uint64_t *d_out)
+{
+    ENTER(ctx);
+    if (nblocks <= 0 || !d_ctr || !d_ct || !d_out) return set_error("cbs_aes128_ctr_transcipher_dev: bad argument"), CBS_ERR_ARG;
+    return dev_ctr(ctx, d_ctr, d_ct, nblocks, d_out);
+}
+
+int cbs_aes128_ctr_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const uint8_t iv[16], const uint64_t *kf_first,
+                               const uint64_t *kf_mid, const uint64_t *kf_last, uint64_t *out)
+{
+    ENTER(ctx);
+    if (nblocks < 0 || (nblocks && (!ct || !out)) || !iv || !kf_first || !kf_mid || !kf_last)
+        return set_error("cbs_aes128_ctr_transcipher: bad argument"), CBS_ERR_ARG;
+    if (!nblocks) return CBS_OK;
+    TRY(cbs_fwd_trans_key_upload(ctx, kf_first, kf_mid, kf_last));
+    // counter blocks: 128-bit big-endian IV + block index (pyaes.Counter, harness/aes_keygen_and_encrypt.py:52)
+    std::vector<uint8_t> ctr((size_t)nblocks * 16);
+    uint8_t cur[16];
+    memcpy(cur, iv, 16);
+    for (int b = 0; b < nblocks; b++) {
+        memcpy(ctr.data() + (size_t)b * 16, cur, 16);
+        for (int i = 15; i >= 0; i--)
+            if (++cur[i] != 0) break;
+    }
+    uint8_t *d_ctr, *d_ct;
+    uint64_t *d_out;
+    TRY(ws_typed(ctx, "io_ctr", (size_t)nblocks * 16, &d_ctr));
+    TRY(ws_typed(ctx, "io_ct", (size_t)nblocks * 16, &d_ct));
+    TRY(ws_typed(ctx, "io_result", (size_t)nblocks * 128 * kLweBig, &d_out));
+    TRY(upload(ctx, d_ctr, ctr.data(), (size_t)nblocks * 16));
+    TRY(upload(ctx, d_ct, ct, (size_t)nblocks * 16));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `ctr` is a local vector
+    TRY(dev_ctr(ctx, d_ctr, d_ct, nblocks, d_out));
     return download(ctx, out, d_out, (size_t)nblocks * 128 * kLweBig * 8);
 }
 

@@ -1406,17 +1406,19 @@ void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts
 // a8: known_rotate_keyed_lut, cbs_lib/src/aes_he.rs:64-93 (rounds 10 + 9: the AES ciphertext byte is
 // public, so the keyed LUT is "rotated" by plain sample extraction at lut_idx*256 + byte).
 // t4 layout [4 mult][nblocks][128][2049]; k10_9 layout [4][16][2][3072]; ct = raw AES ciphertext bytes.
-__global__ void k_known_rotate(const uint8_t *__restrict__ ct, const uint64_t *__restrict__ k10_9,
-                               uint64_t *__restrict__ t4, int nblocks)
+__global__ void k_known_rotate(const uint8_t *__restrict__ ct, const uint64_t *__restrict__ luts,
+                               uint64_t *__restrict__ tm, int nblocks, int inv_shift)
 {
     const int lweid = blockIdx.x;  // (m, blk, i)
     const int i = lweid % 128, blk = (lweid / 128) % nblocks, m = lweid / (128 * nblocks);
     const int byte = i >> 3, bit = i & 7;
-    // cleartext inv_shift_rows of the AES ciphertext (server_encrypted_aes_decryption.rs:89-91,590-597)
+    // inverse direction: cleartext inv_shift_rows of the AES ciphertext first
+    // (server_encrypted_aes_decryption.rs:89-91,590-597); forward direction: SubBytes precedes ShiftRows
     const int row = byte & 3, col = byte >> 2;
-    const int T = (bit & 3) * 256 + ct[blk * 16 + 4 * ((col - row + 4) & 3) + row];
-    const uint64_t *glwe = k10_9 + (size_t)((m * 16 + byte) * 2 + (bit >> 2)) * kGlweWords;
-    uint64_t *o = t4 + (size_t)lweid * kLweBig;
+    const int src = inv_shift ? 4 * ((col - row + 4) & 3) + row : byte;
+    const int T = (bit & 3) * 256 + ct[blk * 16 + src];
+    const uint64_t *glwe = luts + (size_t)((m * 16 + byte) * 2 + (bit >> 2)) * kGlweWords;
+    uint64_t *o = tm + (size_t)lweid * kLweBig;
     for (int w = threadIdx.x; w < 2048; w += blockDim.x) {
         const int c = w >> 10, j = w & 1023;
         const uint64_t *mp = glwe + c * 1024;
@@ -1425,10 +1427,56 @@ __global__ void k_known_rotate(const uint8_t *__restrict__ ct, const uint64_t *_
     if (threadIdx.x == 0) o[2048] = glwe[2048 + T];
 }
 
-void launch_known_rotate(const uint8_t *ct, const uint64_t *k10_9, uint64_t *t4, int nblocks, cudaStream_t s)
+void launch_known_rotate(const uint8_t *ct, const uint64_t *luts, uint64_t *tm, int nblocks, int nmult, int inv_shift,
+                         cudaStream_t s)
 {
     if (nblocks <= 0) return;
-    k_known_rotate<<<4 * nblocks * 128, 256, 0, s>>>(ct, k10_9, t4, nblocks);
+    k_known_rotate<<<nmult * nblocks * 128, 256, 0, s>>>(ct, luts, tm, nblocks, inv_shift);
+}
+
+// forward linear layer: he_shift_rows (cbs_lib/src/aes_he.rs:348-366) on the x1, x2, x3 lists followed by
+// he_mix_columns_precomp (aes_he.rs:441-474), fused into one gather-add.  t3 = [3 (x1,x2,x3)][nblocks][128][2049].
+__global__ void k_fwd_linear(const uint64_t *__restrict__ t3, uint64_t *__restrict__ st, int nblocks)
+{
+    const int lweid = blockIdx.x;
+    const int bit = lweid & 7, byte = (lweid >> 3) & 15, blk = lweid >> 7;
+    const int row = byte & 3, col = byte >> 2;
+    const size_t mult = (size_t)nblocks * 128 * kLweBig;
+    // shifted(r, c) = t(r, (r + c) % 4)
+    auto src = [&](int m, int r) {
+        r &= 3;
+        return t3 + (size_t)m * mult + ((size_t)blk * 128 + (size_t)(4 * ((r + col) & 3) + r) * 8 + bit) * kLweBig;
+    };
+    const uint64_t *p2 = src(1, row), *p3 = src(2, row + 1), *pa = src(0, row + 2), *pb = src(0, row + 3);
+    uint64_t *o = st + (size_t)lweid * kLweBig;
+    for (int w = threadIdx.x; w < kLweBig; w += blockDim.x) o[w] = p2[w] + p3[w] + pa[w] + pb[w];
+}
+
+void launch_fwd_linear(const uint64_t *t3, uint64_t *st, int nblocks, cudaStream_t s)
+{
+    if (nblocks <= 0) return;
+    k_fwd_linear<<<nblocks * 128, 256, 0, s>>>(t3, st, nblocks);
+}
+
+// CTR finish: last-round ShiftRows as a permutation, XOR with the public AES-CTR ciphertext bits
+// (adding bit * 2^63 to the body), and the MSB-first bit order of result.bin.
+__global__ void k_ctr_finish(const uint64_t *__restrict__ in, const uint8_t *__restrict__ ct, uint64_t *__restrict__ out)
+{
+    const int lweid = blockIdx.x;  // destination (blk, byte, msb-first position)
+    const int pos = lweid & 7, byte = (lweid >> 3) & 15, blk = lweid >> 7;
+    const int b = 7 - pos;
+    const int row = byte & 3, col = byte >> 2;
+    const int sbyte = 4 * ((row + col) & 3) + row;
+    const uint64_t *p = in + ((size_t)blk * 128 + sbyte * 8 + b) * kLweBig;
+    uint64_t *o = out + (size_t)lweid * kLweBig;
+    for (int w = threadIdx.x; w < 2048; w += blockDim.x) o[w] = p[w];
+    if (threadIdx.x == 0) o[2048] = p[2048] + ((uint64_t)((ct[blk * 16 + byte] >> b) & 1) << 63);
+}
+
+void launch_ctr_finish(const uint64_t *in, const uint8_t *ct, uint64_t *out, int nblocks, cudaStream_t s)
+{
+    if (nblocks <= 0) return;
+    k_ctr_finish<<<nblocks * 128, 256, 0, s>>>(in, ct, out);
 }
 
 // a9: he_inv_mix_columns_precomp + he_inv_shift_rows, src/bin/server_encrypted_aes_decryption.rs:195-265,

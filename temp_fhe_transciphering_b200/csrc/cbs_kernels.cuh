@@ -65,7 +65,13 @@ void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts
                  const int *out_index, uint64_t *out, int njobs, int accs_per_byte, cudaStream_t s);
 
 // a8  rounds 10+9: sample extraction from the encrypted keyed LUTs (ct = raw AES ciphertext bytes; the cleartext inv_shift_rows is applied inside)
-void launch_known_rotate(const uint8_t *ct, const uint64_t *k10_9, uint64_t *t4, int nblocks, cudaStream_t s);
+//     luts = [nmult][16][2] GLWE, tm = [nmult][nblocks][128][2049]; inv_shift = 1 for the inverse direction
+void launch_known_rotate(const uint8_t *ct, const uint64_t *luts, uint64_t *tm, int nblocks, int nmult, int inv_shift,
+                         cudaStream_t s);
+// forward direction (CTR): ShiftRows + MixColumns-precomp over t3 = [3 (x1,x2,x3)][nblocks][128][2049]
+void launch_fwd_linear(const uint64_t *t3, uint64_t *st, int nblocks, cudaStream_t s);
+// last-round ShiftRows permutation + XOR with the public ciphertext bits + MSB-first order
+void launch_ctr_finish(const uint64_t *in, const uint8_t *ct, uint64_t *out, int nblocks, cudaStream_t s);
 // a9  st = InvShiftRows(InvMixColumns-precomp(t9, t11, t13, t14)), t4 = [4][nblocks][128][2049]
 void launch_inv_linear(const uint64_t *t4, uint64_t *st, int nblocks, cudaStream_t s);
 // final per-byte bit reversal (LSB-first -> MSB-first)

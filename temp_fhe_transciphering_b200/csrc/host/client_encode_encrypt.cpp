@@ -1,6 +1,7 @@
 // client_encode_encrypt <size> [seed] — seeded stand-in for submission/src/bin/client_encode_encrypt.rs:
 // reads datasets/<s>/aes_key.hex and io/<s>/secret_keys/glwe_sk.bin, writes
-// io/<s>/ciphertexts_upload/trans_key.bin (AllRdKeys, src/data_struct.rs:11-26).
+// io/<s>/ciphertexts_upload/trans_key.bin (AllRdKeys, src/data_struct.rs:11-26).  Size 0 (ECB) writes the
+// reference's inverse-direction keys; sizes 1/2 (CTR in the harness) write the forward-direction keys.
 #include "stage_common.h"
 
 int main(int argc, char **argv)
@@ -19,9 +20,16 @@ int main(int argc, char **argv)
     }
     cbs_keyset *ks = nullptr;
     STAGE_TRY(cbs_keyset_load_dir(io_dir.c_str(), 1, &ks));
-    std::vector<uint64_t> k10_9(CBS_K10_9_WORDS), k8_1(CBS_K8_1_WORDS), k0(CBS_K0_WORDS);
-    STAGE_TRY(cbs_trans_key_generate(ks, key.data(), seed, k10_9.data(), k8_1.data(), k0.data()));
-    STAGE_TRY(cbs_trans_key_save((io_dir + "/ciphertexts_upload/trans_key.bin").c_str(), k10_9.data(), k8_1.data(), k0.data()));
+    const std::string out = io_dir + "/ciphertexts_upload/trans_key.bin";
+    if (size == 0) {
+        std::vector<uint64_t> k10_9(CBS_K10_9_WORDS), k8_1(CBS_K8_1_WORDS), k0(CBS_K0_WORDS);
+        STAGE_TRY(cbs_trans_key_generate(ks, key.data(), seed, k10_9.data(), k8_1.data(), k0.data()));
+        STAGE_TRY(cbs_trans_key_save(out.c_str(), k10_9.data(), k8_1.data(), k0.data()));
+    } else {
+        std::vector<uint64_t> kf(CBS_KF_FIRST_WORDS), km(CBS_KF_MID_WORDS), kl(CBS_KF_LAST_WORDS);
+        STAGE_TRY(cbs_fwd_trans_key_generate(ks, key.data(), seed, kf.data(), km.data(), kl.data()));
+        STAGE_TRY(cbs_fwd_trans_key_save(out.c_str(), kf.data(), km.data(), kl.data()));
+    }
     printf("Transciphering keys saved to %s/ciphertexts_upload\n", io_dir.c_str());
     cbs_keyset_free(ks);
     return 0;

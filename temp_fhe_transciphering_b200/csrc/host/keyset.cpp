@@ -343,6 +343,21 @@ struct AesTables {
                 for (int x = 0; x < 256; x++) t[4 * col + row][x] = inv[x ^ rk[10][src]] ^ rk[9][4 * col + row];
             }
     }
+    // forward keyed S-box of round r+1: S(x ^ rk_r[b]) (cbs_lib/src/aes_ref.rs:334-380 get_keyed_sbox*)
+    void lut_fwd(int prev_round, uint8_t t[16][256]) const
+    {
+        for (int b = 0; b < 16; b++)
+            for (int x = 0; x < 256; x++) t[b][x] = sbox[x ^ rk[prev_round][b]];
+    }
+    // last round: S(x ^ rk9[b]) ^ rk10[position b lands on after ShiftRows]
+    void lut_fwd_last(uint8_t t[16][256]) const
+    {
+        for (int col = 0; col < 4; col++)
+            for (int row = 0; row < 4; row++) {
+                const int b = 4 * col + row, dst = 4 * ((col - row + 4) % 4) + row;
+                for (int x = 0; x < 256; x++) t[b][x] = sbox[x ^ rk[9][b]] ^ rk[10][dst];
+            }
+    }
     // get_round_lut / get_0_round_lut (aes_manager.rs:398-432)
     void lut_round(int round, uint8_t t[16][256]) const
     {
@@ -804,6 +819,134 @@ int cbs_trans_key_save(const char *path, const uint64_t *k10_9, const uint64_t *
     if (!w.save(p)) {
         set_error("cannot write " + p);
         return CBS_ERR_IO;
+    }
+    return CBS_OK;
+}
+
+// ---- forward direction (CTR mode) ----
+int cbs_fwd_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *kf_first,
+                               uint64_t *kf_mid, uint64_t *kf_last)
+{
+    if (!ks || ks->glwe_sk.empty() || !aes_key || !kf_first || !kf_mid || !kf_last) {
+        set_error("cbs_fwd_trans_key_generate: needs a keyset with the GLWE secret key");
+        return CBS_ERR_ARG;
+    }
+    AesTables aes(aes_key);
+    static const uint8_t mults[3] = {1, 2, 3};
+    uint8_t tab[16][256];
+    aes.lut_fwd(0, tab);
+    const uint64_t *S = ks->glwe_sk.data();
+    parallel_for(3 * 16 * 2, [&](int id) {
+        const int a = id & 1, b = (id >> 1) & 15, m = id >> 5;
+        Rng rng(seed, 11000 + (uint64_t)id);
+        std::vector<uint64_t> pt(1024);
+        lut_plaintext(pt.data(), tab[b], a, mults[m] == 1 ? 0 : mults[m]);
+        glwe_encrypt(kf_first + (size_t)id * 3072, pt.data(), S, 2, 1024, kStdGlwe, rng);
+    });
+    memset(kf_mid, 0, sizeof(uint64_t) * CBS_KF_MID_WORDS);
+    for (int r = 2; r <= 9; r++) {
+        aes.lut_fwd(r - 1, tab);
+        for (int m = 0; m < 3; m++)
+            for (int b = 0; b < 16; b++)
+                for (int a = 0; a < 2; a++)
+                    lut_plaintext(kf_mid + ((((size_t)(r - 2) * 3 + m) * 16 + b) * 2 + a) * 3072 + 2048, tab[b], a,
+                                  mults[m] == 1 ? 0 : mults[m]);
+    }
+    memset(kf_last, 0, sizeof(uint64_t) * CBS_KF_LAST_WORDS);
+    aes.lut_fwd_last(tab);
+    for (int b = 0; b < 16; b++)
+        for (int a = 0; a < 2; a++) lut_plaintext(kf_last + ((size_t)b * 2 + a) * 3072 + 2048, tab[b], a, 0);
+    return CBS_OK;
+}
+
+// Forward keys use the AllRdKeys bincode shape with 3-tuples (x1, x2, x3) and 8 middle rounds.
+int cbs_fwd_trans_key_save(const char *path, const uint64_t *kf_first, const uint64_t *kf_mid, const uint64_t *kf_last)
+{
+    if (!path) return CBS_ERR_ARG;
+    Writer w;
+    w.buf.reserve(22000000);
+    for (int m = 0; m < 3; m++) {
+        w.u64(16);
+        for (int b = 0; b < 16; b++) {
+            w.vec(kf_first + ((size_t)m * 16 + b) * 2 * 3072, 2 * 3072);
+            w.u64(3);
+            w.u64(1024);
+            w.modulus();
+        }
+    }
+    w.u64(8);
+    for (int rd = 0; rd < 8; rd++)
+        for (int m = 0; m < 3; m++) {
+            w.u64(16);
+            for (int b = 0; b < 16; b++) {
+                w.u64(2);
+                for (int a = 0; a < 2; a++) {
+                    w.vec(kf_mid + ((((size_t)rd * 3 + m) * 16 + b) * 2 + a) * 3072, 3072);
+                    w.u64(1024);
+                    w.modulus();
+                }
+            }
+        }
+    w.u64(16);
+    for (int b = 0; b < 16; b++) {
+        w.u64(2);
+        for (int a = 0; a < 2; a++) {
+            w.vec(kf_last + ((size_t)b * 2 + a) * 3072, 3072);
+            w.u64(1024);
+            w.modulus();
+        }
+    }
+    std::string p(path);
+    size_t slash = p.find_last_of('/');
+    if (slash != std::string::npos) mkdirs(p.substr(0, slash));
+    if (!w.save(p)) {
+        set_error("cannot write " + p);
+        return CBS_ERR_IO;
+    }
+    return CBS_OK;
+}
+
+int cbs_fwd_trans_key_load(const char *path, uint64_t *kf_first, uint64_t *kf_mid, uint64_t *kf_last)
+{
+    Reader r;
+    if (!path || !r.load(path)) {
+        set_error(std::string("cannot read ") + (path ? path : "(null)"));
+        return CBS_ERR_IO;
+    }
+    for (int m = 0; m < 3; m++) {
+        r.expect(16);
+        for (int b = 0; b < 16; b++) {
+            r.vec_into(kf_first + ((size_t)m * 16 + b) * 2 * 3072, 2 * 3072);
+            r.expect(3);
+            r.expect(1024);
+            r.modulus();
+        }
+    }
+    r.expect(8);
+    for (int rd = 0; rd < 8; rd++)
+        for (int m = 0; m < 3; m++) {
+            r.expect(16);
+            for (int b = 0; b < 16; b++) {
+                r.expect(2);
+                for (int a = 0; a < 2; a++) {
+                    r.vec_into(kf_mid + ((((size_t)rd * 3 + m) * 16 + b) * 2 + a) * 3072, 3072);
+                    r.expect(1024);
+                    r.modulus();
+                }
+            }
+        }
+    r.expect(16);
+    for (int b = 0; b < 16; b++) {
+        r.expect(2);
+        for (int a = 0; a < 2; a++) {
+            r.vec_into(kf_last + ((size_t)b * 2 + a) * 3072, 3072);
+            r.expect(1024);
+            r.modulus();
+        }
+    }
+    if (!r.done()) {
+        set_error(std::string(path) + ": not a forward (CTR) transciphering key for AES_TIGHT");
+        return CBS_ERR_FORMAT;
     }
     return CBS_OK;
 }

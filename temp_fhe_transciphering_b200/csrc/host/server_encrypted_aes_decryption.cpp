@@ -4,9 +4,13 @@
 // io/<s>/ciphertexts_upload/trans_key.bin) and output (io/<s>/ciphertext_aes_download/result.bin).
 // The reference transciphers only the first 16-byte block of db.hex (:613-617); this binary
 // transciphers every block, sharded contiguously over the visible GPUs (CBS_GPUS limits the count).
+// Mode follows the harness (harness/aes_keygen_and_encrypt.py:45-55): size 0 = ECB block decryption
+// with the reference's AllRdKeys; sizes 1/2 = CTR with datasets/<s>/aes_iv.hex and the forward-direction
+// transciphering key written by our client_encode_encrypt (the reference has no CTR path).
 #include "stage_common.h"
 
 #include <algorithm>
+#include <cstring>
 #include <thread>
 
 int main(int argc, char **argv)
@@ -25,9 +29,17 @@ int main(int argc, char **argv)
 
     cbs_keyset *ks = nullptr;
     STAGE_TRY(cbs_keyset_load_dir(io_dir.c_str(), 0, &ks));
-    std::vector<uint64_t> k10_9(CBS_K10_9_WORDS), k8_1(CBS_K8_1_WORDS), k0(CBS_K0_WORDS);
-    STAGE_TRY(cbs_trans_key_load((io_dir + "/ciphertexts_upload/trans_key.bin").c_str(), k10_9.data(), k8_1.data(),
-                                 k0.data()));
+    const bool ctr_mode = size >= 1;
+    std::vector<uint8_t> iv;
+    if (ctr_mode && (!read_hex_file(data_dir + "/aes_iv.hex", iv) || iv.size() != 16)) {
+        fprintf(stderr, "Error: cannot read %s/aes_iv.hex\n", data_dir.c_str());
+        return 1;
+    }
+    std::vector<uint64_t> k10_9(ctr_mode ? CBS_KF_FIRST_WORDS : CBS_K10_9_WORDS),
+        k8_1(ctr_mode ? CBS_KF_MID_WORDS : CBS_K8_1_WORDS), k0(CBS_K0_WORDS);
+    const std::string tk_path = io_dir + "/ciphertexts_upload/trans_key.bin";
+    if (ctr_mode) STAGE_TRY(cbs_fwd_trans_key_load(tk_path.c_str(), k10_9.data(), k8_1.data(), k0.data()));
+    else STAGE_TRY(cbs_trans_key_load(tk_path.c_str(), k10_9.data(), k8_1.data(), k0.data()));
 
     int ngpu = 0;
     if (cbs_device_count(&ngpu) != CBS_OK || ngpu == 0) {
@@ -46,9 +58,21 @@ int main(int argc, char **argv)
             const int b0 = (int)((long)nblocks * g / ngpu), b1 = (int)((long)nblocks * (g + 1) / ngpu);
             cbs_ctx *ctx = nullptr;
             rc[g] = cbs_ctx_create(ks, g, &ctx);
-            if (rc[g] == CBS_OK)
+            if (rc[g] == CBS_OK && !ctr_mode)
                 rc[g] = cbs_aes128_transcipher(ctx, ct.data() + (size_t)b0 * 16, b1 - b0, k10_9.data(), k8_1.data(), k0.data(),
                                                result.data() + (size_t)b0 * 128 * CBS_LWE_BIG_WORDS);
+            if (rc[g] == CBS_OK && ctr_mode) {
+                uint8_t civ[16];  // counter of this shard's first block: IV + b0 (128-bit big-endian)
+                memcpy(civ, iv.data(), 16);
+                unsigned carry = (unsigned)b0;
+                for (int i = 15; i >= 0 && carry; i--) {
+                    carry += civ[i];
+                    civ[i] = (uint8_t)carry;
+                    carry >>= 8;
+                }
+                rc[g] = cbs_aes128_ctr_transcipher(ctx, ct.data() + (size_t)b0 * 16, b1 - b0, civ, k10_9.data(), k8_1.data(),
+                                                   k0.data(), result.data() + (size_t)b0 * 128 * CBS_LWE_BIG_WORDS);
+            }
             if (rc[g] != CBS_OK) err[g] = cbs_last_error();
             cbs_ctx_destroy(ctx);
         });

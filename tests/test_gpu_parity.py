@@ -186,6 +186,23 @@ def test_aes_transcipher_two_blocks(ctx, orc, orc_keys, keyset, aes_key, trans_k
     assert abs(std - ostd) < 0.5
 
 
+def test_aes_ctr_transcipher(ctx, orc, orc_keys, keyset, aes_key):
+    """CTR mode (harness sizes 1/2): forward AES of the public counters xor the ciphertext."""
+    import aes_clear
+    import ref_io
+    iv = bytes([0xFF] * 15 + [0xFE])  # exercises the 128-bit big-endian carry on the 3rd block
+    pt = bytes(np.random.default_rng(12).integers(0, 256, 48, dtype=np.uint8))
+    ct = aes_clear.ctr_crypt(aes_key, iv, pt)
+    kf = keyset.gen_forward_transciphering_keys(aes_key, 55)
+    got = ctx.aes_ctr_to_lwe_transciphering(ct, iv, *kf)
+    bits, std, mx = ref_io.noise_stats(got.reshape(-1, 2049), keyset.glwe_sk)
+    assert np.packbits(bits).tobytes() == pt
+    assert std < 58.5 and mx < 61.0, (std, mx)
+    want = orc.aes128_ctr_transcipher(orc_keys, ct[:16], iv, *kf)
+    obits, ostd, _ = ref_io.noise_stats(want[0], keyset.glwe_sk)
+    assert (obits == bits[:128]).all() and abs(std - ostd) < 0.5
+
+
 def test_max_u16(ctx, keyset):
     import ref_io
     vals = [20962, 11749, 64797, 2177, 19876, 44457, 4094, 20862]

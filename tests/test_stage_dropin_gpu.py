@@ -47,3 +47,36 @@ def test_reference_clients_around_our_servers(tmp_path, nvals):
     # same bytes on disk as the reference writes: LweCiphertextList of 128 x blocks / 16 ciphertexts
     assert os.path.getsize(d / "io" / "toy" / "ciphertext_aes_download" / "result.bin") == 8 + nvals * 16 * 2049 * 8 + 32
     assert os.path.getsize(d / "io" / "toy" / "ciphertexts_download" / "result.bin") == 262_312
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "client_key_generation")), reason="oracle/_ref not built")
+def test_small_instance_ctr_mode(tmp_path):
+    """Harness size 1 ("small": 64 u16 = 8 blocks, AES-CTR; harness/aes_keygen_and_encrypt.py:49-55):
+    reference key generation and decryption clients, OUR client_encode_encrypt (forward keys; the
+    reference's only emits ECB-decryption keys) and OUR two servers."""
+    import aes_clear
+    rng = np.random.default_rng(64)
+    vals = rng.integers(0, 65536, 64).tolist()
+    key, iv = aes_clear.harness_aes_key(None), aes_clear.harness_iv(None)
+    ct = aes_clear.ctr_crypt(key, iv, aes_clear.pack_u16_be(vals))
+    d = tmp_path
+    os.makedirs(d / "datasets" / "small")
+    (d / "datasets" / "small" / "aes_key.hex").write_text(key.hex())
+    (d / "datasets" / "small" / "aes_iv.hex").write_text(iv.hex())
+    (d / "datasets" / "small" / "db.hex").write_text(ct.hex())
+
+    def run(exe, *args):
+        subprocess.run([exe, "1", *args], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=900)
+
+    run(os.path.join(REF, "client_key_generation"))
+    run(os.path.join(BIN, "client_encode_encrypt"))
+    run(os.path.join(BIN, "server_encrypted_aes_decryption"))
+    run(os.path.join(BIN, "server_encrypted_compute"))
+    run(os.path.join(REF, "client_decrypt_decode_aes_decryption"))
+    run(os.path.join(REF, "client_postprocess_aes_decryption"))
+    run(os.path.join(REF, "client_decrypt_decode"))
+    run(os.path.join(REF, "client_postprocess"))
+    got = [int(x) for x in (d / "io" / "small" / "result_aes.txt").read_text().split()]
+    got_max = [int(x) for x in (d / "io" / "small" / "result.txt").read_text().split()]
+    assert got == vals
+    assert got_max == [max(vals)]
