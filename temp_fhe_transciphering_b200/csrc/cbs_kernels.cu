@@ -638,20 +638,33 @@ __device__ __forceinline__ void fill_t2_table(cplx *t2tab, const double *twtab, 
 }
 
 constexpr int kBr3GroupSmem = kGlweWords * 8 + 2 * 512 * 16;                         // 40 KB
-constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes + 64;  // + mbarriers
+constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes + 64 + kBrGroups * kLweN * 2;  // + mbarriers + rotations
 
+template <bool PROF>
 __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uint64_t *__restrict__ lwe,
                                                                         uint64_t *__restrict__ acc_out, int count,
                                                                         const double *__restrict__ bsk_f,
-                                                                        const double *__restrict__ twtab)
+                                                                        const double *__restrict__ twtab, int groups,
+                                                                        int ct_base, unsigned long long *prof)
 {
+    // PROF: per-phase clock64() totals of thread 0 of CTA 0 (development aid, CBS_BR_PROF=1)
+    long long pc[6] = {0, 0, 0, 0, 0, 0};
+    long long t0 = 0;
+#define PROF_MARK(k)                         \
+    if (PROF) {                              \
+        long long now = clock64();           \
+        pc[k] += now - t0;                   \
+        t0 = now;                            \
+    }
+    // `groups` (<= kBrGroups) ciphertexts per CTA, first ciphertext of the launch = ct_base; `count` is the
+    // exclusive upper bound.  The launcher uses groups < kBrGroups to balance the last wave.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int gi = threadIdx.x >> 6;
-    const int ct = blockIdx.x * kBrGroups + gi;
+    const int ct = (gi < groups) ? ct_base + blockIdx.x * groups + gi : count;
     unsigned char *ring = smem_raw + (size_t)kBrGroups * kBr3GroupSmem;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes);
     uint64_t *empty = full + kBrRing;
-    const int active_groups = min(kBrGroups, count - blockIdx.x * kBrGroups);
+    const int active_groups = min(groups, count - (ct_base + blockIdx.x * groups));
     if (threadIdx.x == 0) {
         for (int b = 0; b < kBrRing; b++) {
             mbar_init(full + b, 1);
@@ -675,6 +688,9 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
     cplx *scr1 = scr0 + 512;
     int flip = 0;
     const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+    // all 768 mod-switched rotation amounts up front: no global-load latency inside the step loop
+    uint16_t *rot = reinterpret_cast<uint16_t *>(ring + kBrRing * kBrTileBytes + 64) + gi * kLweN;
+    for (int q = t; q < kLweN; q += 64) rot[q] = (uint16_t)(modswitch_dev(a[q]) & 2047);
     {
         const int bt = modswitch_dev(a[kLweN]);
         for (int jj = t; jj < 512; jj += 64) {
@@ -702,8 +718,9 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
     int tile = 0;
 #pragma unroll 1
     for (int i = 0; i < kLweN; i++) {
-        const int d = modswitch_dev(__ldg(a + i)) & 2047;
+        const int d = rot[i];
         const bool skip = (d == 0);
+        if (PROF) t0 = clock64();
         cplx out[3][8];
 #pragma unroll
         for (int c = 0; c < 3; c++)
@@ -736,6 +753,7 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                     if (h == 1 || h == 2) rh = 0ull - rh;
                     v[m] = cplx{i32_to_double(digit_b23_l1(rl - own.lo)), i32_to_double(digit_b23_l1(rh - own.hi))};
                 }
+                PROF_MARK(0);  // build
                 cplx *s = flip ? scr1 : scr0;
                 flip ^= 1;
                 fwd_p1(v, s, tw, t);
@@ -743,7 +761,9 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                 fwd_p2(v, s, tw, t);
                 group_sync(bar);
                 const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
+                PROF_MARK(1);  // forward passes 1-2
                 mbar_wait(full + buf, use & 1);  // requested a whole FFT ago: normally already complete
+                PROF_MARK(2);  // tile wait
                 cplx kc[8], kn[8];
 #pragma unroll
                 for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];  // column 0, overlaps the last pass
@@ -759,6 +779,7 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
 #pragma unroll
                     for (int k3 = 0; k3 < 8; k3++) kc[k3] = kn[k3];
                 }
+                PROF_MARK(3);  // pass 3 + multiply-accumulate
             } else {
                 mbar_wait(full + buf, use & 1);
             }
@@ -774,6 +795,7 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
             inv_p2(out[c], s, tw, t);
             group_sync(bar);
             inv_p1(out[c], s, tw, t);
+            PROF_MARK(4);  // inverse transform
             u64x2 *p = acc + c * 512;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
@@ -782,8 +804,12 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                 w.hi += torus_from_scaled(out[c][m].y);
                 p[t + 64 * m] = w;
             }
+            PROF_MARK(5);  // torus rounding + accumulator update
         }
     }
+    if (PROF && prof && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int k = 0; k < 6; k++) prof[k] = (unsigned long long)pc[k];
+#undef PROF_MARK
     group_sync(bar);
     uint64_t *o = acc_out + (size_t)ct * kGlweWords;
     for (int w = t; w < 3 * 512; w += 64) {
@@ -793,6 +819,18 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
         o[c * 1024 + jj + 512] = x.hi;
     }
 }
+
+// Other decompositions measured on B200 and rejected (tools/brbench.py, 1024 ciphertexts):
+//   * one polynomial per 64-thread sub-group, three sub-groups per ciphertext, spectra exchanged through
+//     the transpose tiles (per-step latency 15.9 k -> 9.3 k cycles, but only 2 ciphertexts fit per SM):
+//     14.2 ms vs 12.4 ms;
+//   * five groups per CTA with a single transpose tile: ptxas caps 320 threads at 168 registers, 472 B of
+//     spills: 23.6 ms;
+//   * three polynomials in flight per group with 3 groups per CTA (ILP instead of occupancy): 18.5 ms;
+//   * pass-2 twiddles in a shared table: 13.3 ms; balancing the last wave with 3-group CTAs: -2 % only,
+//     because a group's step is a latency chain that does not speed up when its neighbours leave.
+// Per-step cycle budget of a v3 group (CBS_BR_PROF=1): build 4.2 k, forward passes 3.3 k, pass 3 + MAC 2.8 k,
+// inverse 4.2 k, torus + update 1.5 k, tile wait 0.5 k.
 
 static int br_variant()
 {
@@ -811,7 +849,8 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     if (!attr) {
         cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrTmaSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         attr = true;
     }
     const int grid = (count + kBrGroups - 1) / kBrGroups;
@@ -819,8 +858,36 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
     else if (br_variant() == 1)
         k_blind_rotate_tma<<<grid, 64 * kBrGroups, kBrTmaSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-    else
-        k_blind_rotate_v3<<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+    else {
+        static int split = -1, sms = 0;
+        if (split < 0) {
+            const char *e = getenv("CBS_BR_SPLIT");
+            split = e ? atoi(e) : 0;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const int full_wave = sms * kBrGroups;
+        const int rem = count % full_wave;
+        // last-wave balancing: a remainder that fits sms x 3 (or x 2) groups runs with fewer groups per SM
+        if (split && count > full_wave && rem > 0 && rem <= sms * (kBrGroups - 1)) {
+            const int head = count - rem;
+            const int g = (rem + sms - 1) / sms;  // groups per CTA in the tail launch
+            k_blind_rotate_v3<false><<<head / kBrGroups, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw, kBrGroups, 0, nullptr);
+            k_blind_rotate_v3<false><<<(rem + g - 1) / g, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, g, head, nullptr);
+        } else if (getenv("CBS_BR_PROF")) {
+            static unsigned long long *d_prof = nullptr;
+            if (!d_prof) cudaMalloc(&d_prof, 6 * sizeof(unsigned long long));
+            k_blind_rotate_v3<true><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, kBrGroups, 0, d_prof);
+            unsigned long long h[6];
+            cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            fprintf(stderr, "[br prof] cycles: build %llu  fwd12 %llu  tilewait %llu  p3+mac %llu  inverse %llu  torus %llu\n", h[0], h[1],
+                    h[2], h[3], h[4], h[5]);
+        } else {
+            k_blind_rotate_v3<false><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, kBrGroups, 0, nullptr);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
