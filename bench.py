@@ -34,6 +34,22 @@ METRIC = "AES-128 blocks transciphered/sec"
 UNIT = "blocks/s"
 
 
+def read_ncu_traffic():
+    """DRAM bytes per blind-rotation launch from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_final_ncu_full.csv")
+    try:
+        rd = wr = None
+        for line in open(p):
+            f = line.strip().split(",")
+            if f[0] == "dram__bytes_read.sum":
+                rd = float(f[2]) * (1e6 if f[1] == "Mbyte" else 1e9 if f[1] == "Gbyte" else 1e3 if f[1] == "Kbyte" else 1)
+            if f[0] == "dram__bytes_write.sum":
+                wr = float(f[2]) * (1e6 if f[1] == "Mbyte" else 1e9 if f[1] == "Gbyte" else 1e3 if f[1] == "Kbyte" else 1)
+        return None if rd is None or wr is None else rd + wr
+    except Exception:
+        return None
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -319,6 +335,19 @@ def main_ours(args):
     h2d = 16 * nblocks + 8 * (cbs.K10_9_WORDS + cbs.K8_1_WORDS + cbs.K0_WORDS)
     d2h = nblocks * 128 * 2049 * 8
 
+    # --- mini-workload of the small instance: encrypted max over the 8*nblocks transciphered u16 values
+    #     (stage 8, server_encrypted_compute.rs), host buffers through the C ABI; reported, not part of `value` ---
+    maxw = None
+    if rank == 0:
+        res = h_out_t.numpy().view(np.uint64).reshape(-1, 2049)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mx_ct = ctx.max_u16(res)
+        t_max = time.perf_counter() - t0
+        got = ref_io.bits_to_u16(ref_io.decode_bit(ref_io.lwe_phase(mx_ct, ks.glwe_sk)))[0]
+        want = max(aes_clear.unpack_u16_be(pt))
+        maxw = {"values": 8 * nblocks, "seconds": t_max, "verified": bool(got == want)}
+
     # --- roofline of the dominant kernel (blind rotation), timed alone with CUDA events ---
     roof = None
     cpu = None
@@ -343,7 +372,8 @@ def main_ours(args):
         br_bytes = BSK_BYTES + B * BR_IO_BYTES
         roof = {
             "kernel": "k_blind_rotate", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp64_peak, "traffic": None, "peak_source": "FP64 FMA probe kernel, same run",
+            "frac": achieved / fp64_peak, "traffic": read_ncu_traffic(),
+            "traffic_source": "profiles/r01_final_ncu_full.csv (ncu --set full, same kernel and batch)", "peak_source": "FP64 FMA probe kernel, same run",
             "launch_ms": br_ms, "ciphertexts_per_launch": B, "share_of_step": br_ms * 9 / (ms_total / args.steps),
             "hbm": {"bound": "hbm", "achieved": br_bytes / (br_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": br_bytes / (br_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src + " MEASURED_PEAKS.json",
@@ -373,6 +403,7 @@ def main_ours(args):
             "clocks": clocks,
             "verified": bool(verified), "output_noise_log2_std": std, "output_noise_log2_max": mx,
             "roofline": roof,
+            "max_u16_miniworkload": maxw,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
