@@ -1194,6 +1194,215 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v2(const uint64_t *
     }
 }
 
+// ---- trace v3: v2 + automorphism-key tiles staged through a TMA ring --------------------------------
+// ncu r01 (profiles/r01_final_ncu_full.csv) on v2: long-scoreboard (48 dependent 16-byte key loads from L2
+// per thread per digit level) was the top stall at 31 % of warp time.  The four key tiles of a digit
+// level - (input poly i, limb) in {0,1}^2, 24,576 B each - are now fetched once per CTA with
+// cp.async.bulk into four single-slot lanes guarded by full/empty mbarriers and shared by the two GLWE
+// units of the CTA; the request for level n+1 is issued right after level n is released, one whole
+// transform before its use.  Shared memory is found by single-buffering the spectrum exchange (one
+// extra 128-thread barrier per level) and using one transpose tile per sub-group (the unit barriers
+// already order every tile reuse).
+constexpr int kTr3UnitSmem = kGlweWords * 8 + 2 * 8192 + 2 * 8192;  // cur 24 KB + 2 tiles + exchange = 56 KB
+constexpr int kTr3SmemBytes = kTr2Glwe * kTr3UnitSmem + 4 * kBrTileBytes + 1024 + 64;
+
+__global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *__restrict__ in,
+                                                                 uint64_t *__restrict__ out, int count, int from_acc,
+                                                                 const double *__restrict__ auto_f,
+                                                                 const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gl = threadIdx.x >> 7;
+    const int sub = (threadIdx.x >> 6) & 1;
+    const int t = threadIdx.x & 63;
+    const int idx = blockIdx.x * kTr2Glwe + gl;
+    unsigned char *ring = smem_raw + (size_t)kTr2Glwe * kTr3UnitSmem;  // lane (i, limb) at (limb*2 + i) * 24,576
+    cplx *t2tab = reinterpret_cast<cplx *>(ring + 4 * kBrTileBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + 4 * kBrTileBytes + 1024);
+    uint64_t *empty = full + 4;
+    const int active_units = min(kTr2Glwe, count - blockIdx.x * kTr2Glwe);
+    fill_t2_table(t2tab, twtab, threadIdx.x);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 4; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, 64 * active_units);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (idx >= count) return;
+    const bool producer = (threadIdx.x == 0);
+    const char *key_bytes = reinterpret_cast<const char *>(auto_f);
+    // tile of use n = s*3 + tt (level lev = 2 - tt), lane (i, sp): Fourier polys [s][i][sp][lev][0..2]
+    auto tile_src = [&](int n, int i, int sp) {
+        const int s = n / 3, lev = 2 - (n % 3);
+        return key_bytes + (size_t)((((s * 2 + i) * 2 + sp) * 3 + lev) * 3) * kFourierPolyDoubles * 8;
+    };
+    auto produce = [&](int n) {
+        if (n >= 30) return;
+#pragma unroll
+        for (int L = 0; L < 4; L++) {
+            if (n > 0) mbar_wait(empty + L, (n - 1) & 1);
+            tma_load_tile(ring + L * kBrTileBytes, tile_src(n, L & 1, L >> 1), kBrTileBytes, full + L);
+        }
+    };
+    if (producer) produce(0);
+    int want = -1;  // next ring refill the producer owes (issued one barrier into the following transform)
+
+    const cplx *t2s = t2tab + (t & 7);
+    unsigned char *base = smem_raw + (size_t)gl * kTr3UnitSmem;
+    u64x2 *cur = reinterpret_cast<u64x2 *>(base);
+    cplx *scr = reinterpret_cast<cplx *>(base + kGlweWords * 8 + sub * 8192);
+    cplx *X = reinterpret_cast<cplx *>(base + kGlweWords * 8 + 16384);  // [sub 2][512]
+    const int sbar = 1 + gl * 2 + sub;
+    const int ubar = 5 + gl;
+    Twiddles tw;
+    load_twiddles(tw, twtab, t);
+    {
+        const int u = threadIdx.x & 127;
+        if (from_acc) {
+            const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
+            const int lvl = idx % kCbsLevel;
+            for (int w = u; w < 3 * 512; w += 128) {
+                const int p = w >> 9, jj = w & 511;
+                cur[w] = u64x2{glev_pre_word(acc, lvl, p, jj), glev_pre_word(acc, lvl, p, jj + 512)};
+            }
+        } else {
+            const uint64_t *src = in + (size_t)idx * kGlweWords;
+            for (int w = u; w < 3 * 512; w += 128) {
+                const int p = w >> 9, jj = w & 511;
+                cur[w] = u64x2{src[p * 1024 + jj], src[p * 1024 + jj + 512]};
+            }
+        }
+    }
+    unit_sync(ubar);
+
+#pragma unroll 1
+    for (int s = 0; s < 10; s++) {
+        const int kinv = c_kappa_inv[s];
+        uint64_t pk[16];
+        {
+            const u64x2 *p = cur + sub * 512;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int jj = t + 64 * m;
+                const int e = (jj * kinv) & 2047;
+                const u64x2 A = p[e & 511];
+                const int h = e >> 9;
+                pk[2 * m] = pack_digits<13, 3, uint64_t>(pair_pick(A, h));
+                pk[2 * m + 1] = pack_digits<13, 3, uint64_t>(pair_pick(A, (h + kinv) & 3));
+            }
+        }
+        u64x2 nb[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int jj = t + 64 * (4 * sub + q);
+            const int e = (jj * kinv) & 2047;
+            const u64x2 A = cur[1024 + (e & 511)];
+            const int h = e >> 9;
+            const u64x2 own = cur[1024 + jj];
+            nb[q] = u64x2{own.lo + pair_pick(A, h), own.hi + pair_pick(A, (h + kinv) & 3)};
+        }
+        unit_sync(ubar);
+#pragma unroll
+        for (int q = 0; q < 4; q++) cur[1024 + t + 64 * (4 * sub + q)] = nb[q];
+
+        cplx acc[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+        for (int tt = 0; tt < 3; tt++) {
+            const int n = s * 3 + tt;
+            cplx v[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m], tt)),
+                            i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m + 1], tt))};
+            fwd_p1(v, scr, tw, t);
+            group_sync(sbar);
+            if (producer && want >= 0) {
+                produce(want);
+                want = -1;
+            }
+            fwd_p2_s(v, scr, t2s, t);
+            group_sync(sbar);
+            fwd_p3(v, scr, t);
+            cplx *Xw = X + sub * 512 + t;
+            const cplx *Xr = X + (1 - sub) * 512 + t;
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) Xw[k3 * 64] = v[k3];
+            unit_sync(ubar);
+            // own spectrum x key(i = sub, limb = sub), partner spectrum x key(i = 1 - sub, limb = sub)
+            const int Lown = sub * 2 + sub, Loth = sub * 2 + (1 - sub);
+            mbar_wait(full + Lown, n & 1);
+            {
+                const cplx *key = reinterpret_cast<const cplx *>(ring + Lown * kBrTileBytes) + t;
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int k3 = 0; k3 < 8; k3++) cfma(acc[c][k3], v[k3], key[c * 512 + k3 * 64]);
+            }
+            mbar_arrive(empty + Lown);
+            mbar_wait(full + Loth, n & 1);
+            {
+                const cplx *key = reinterpret_cast<const cplx *>(ring + Loth * kBrTileBytes) + t;
+#pragma unroll
+                for (int k3 = 0; k3 < 8; k3++) {
+                    const cplx o = Xr[k3 * 64];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) cfma(acc[c][k3], o, key[c * 512 + k3 * 64]);
+                }
+            }
+            mbar_arrive(empty + Loth);
+            want = n + 1;
+            unit_sync(ubar);  // partner finished reading the exchange tile before it is rewritten
+        }
+        const int shift = sub ? 41 : 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_p3(acc[c], scr, t);
+            group_sync(sbar);
+            if (producer && want >= 0) {
+                produce(want);
+                want = -1;
+            }
+            inv_p2_s(acc[c], scr, t2s, t);
+            group_sync(sbar);
+            inv_p1(acc[c], scr, tw, t);
+            u64x2 *p = cur + c * 512;
+            if (sub == 0) {
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    u64x2 w = p[t + 64 * m];
+                    w.lo += torus_from_scaled(acc[c][m].x);
+                    w.hi += torus_from_scaled(acc[c][m].y);
+                    p[t + 64 * m] = w;
+                }
+            }
+            unit_sync(ubar);
+            if (sub == 1) {
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    u64x2 w = p[t + 64 * m];
+                    w.lo += torus_from_scaled(acc[c][m].x) << shift;
+                    w.hi += torus_from_scaled(acc[c][m].y) << shift;
+                    p[t + 64 * m] = w;
+                }
+            }
+        }
+        unit_sync(ubar);
+    }
+    uint64_t *dst = out + (size_t)idx * kGlweWords;
+    for (int w = threadIdx.x & 127; w < 3 * 512; w += 128) {
+        const u64x2 x = cur[w];
+        const int c = w >> 9, jj = w & 511;
+        dst[c * 1024 + jj] = x.lo;
+        dst[c * 1024 + jj + 512] = x.hi;
+    }
+}
+
 void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int count, int from_acc, cudaStream_t s)
 {
     if (count <= 0) return;
@@ -1210,14 +1419,18 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
         cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
         cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmemBytes);
         cudaFuncSetAttribute(k_trace_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr2SmemBytes);
+        cudaFuncSetAttribute(k_trace_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
         init = true;
     }
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("CBS_TRACE_VARIANT");
-        variant = e ? atoi(e) : 2;
+        variant = e ? atoi(e) : 3;
     }
-    if (variant == 1)
+    if (variant == 3)
+        k_trace_v3<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
+                                                                                               K.auto_f, K.tw);
+    else if (variant == 1)
         k_trace<<<(count + kTrGroups - 1) / kTrGroups, 64 * kTrGroups, kTrSmemBytes, s>>>(in, out, count, from_acc, K.auto_f,
                                                                                            K.tw);
     else
