@@ -41,6 +41,9 @@ struct cbs_ctx {
     bool have_trans_key = false;
     uint64_t *d_kf_first = nullptr, *d_kf_mid = nullptr, *d_kf_last = nullptr;
     bool have_fwd_key = false;
+    // every mask word of the round 8..1 / round 0 LUTs is zero (always true for AllRdKeys written by the
+    // reference, src/data_struct.rs:145-151,258-263); checked at upload, enables the first-CMux shortcut
+    int inv_luts_trivial = 0, fwd_luts_trivial = 0;
     int jobs24_nblocks = -1;
     std::map<std::string, DevBuf> ws;
     // cached LUT job tables, keyed by block count
@@ -49,6 +52,18 @@ struct cbs_ctx {
 };
 
 namespace {
+
+// true if every GLWE in `luts` (count x 3072 words) has all-zero mask polynomials
+int all_masks_zero(const uint64_t *luts, size_t count)
+{
+    for (size_t g = 0; g < count; g++) {
+        const uint64_t *m = luts + g * kGlweWords;
+        uint64_t acc = 0;
+        for (int j = 0; j < 2048; j++) acc |= m[j];
+        if (acc) return 0;
+    }
+    return 1;
+}
 
 #define CUDA_TRY(expr)                                                                                   \
     do {                                                                                                 \
@@ -237,7 +252,7 @@ int dev_transcipher_chunk(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d
         TRY(dev_keyswitch(ctx, d_st, d_ks, B));
         TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
         const uint64_t *luts = ctx->d_k8_1 + (size_t)(round - 1) * 4 * 16 * 2 * kGlweWords;
-        launch_lut8(ctx->K, d_ggsw_f, luts, lut32, out32, d_t4, nb * 16 * 8, 8, ctx->stream);
+        launch_lut8(ctx->K, d_ggsw_f, luts, lut32, out32, d_t4, nb * 16 * 8, 8, ctx->inv_luts_trivial, ctx->stream);
         launch_inv_linear(d_t4, d_st, nb, ctx->stream);
         ctx->launches += 2;
         TRY(check_launch("round"));
@@ -245,7 +260,7 @@ int dev_transcipher_chunk(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d
     // last round (:166-180) + per-byte bit reversal (:182-189)
     TRY(dev_keyswitch(ctx, d_st, d_ks, B));
     TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
-    launch_lut8(ctx->K, d_ggsw_f, ctx->d_k0, lut8, out8, d_st, nb * 16 * 2, 2, ctx->stream);
+    launch_lut8(ctx->K, d_ggsw_f, ctx->d_k0, lut8, out8, d_st, nb * 16 * 2, 2, ctx->inv_luts_trivial, ctx->stream);
     launch_reverse_bits(d_st, d_out, nb, ctx->stream);
     ctx->launches += 2;
     return check_launch("last round");
@@ -290,14 +305,14 @@ int dev_ctr_chunk(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int n
         TRY(dev_keyswitch(ctx, d_st, d_ks, B));
         TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
         const uint64_t *luts = ctx->d_kf_mid + (size_t)(round - 2) * 3 * 16 * 2 * kGlweWords;
-        launch_lut8(ctx->K, d_ggsw_f, luts, lut24, out24, d_t3, j24, 6, ctx->stream);
+        launch_lut8(ctx->K, d_ggsw_f, luts, lut24, out24, d_t3, j24, 6, ctx->fwd_luts_trivial, ctx->stream);
         launch_fwd_linear(d_t3, d_st, nb, ctx->stream);
         ctx->launches += 2;
         TRY(check_launch("ctr round"));
     }
     TRY(dev_keyswitch(ctx, d_st, d_ks, B));
     TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
-    launch_lut8(ctx->K, d_ggsw_f, ctx->d_kf_last, lut8, out8, d_st, nb * 16 * 2, 2, ctx->stream);
+    launch_lut8(ctx->K, d_ggsw_f, ctx->d_kf_last, lut8, out8, d_st, nb * 16 * 2, 2, ctx->fwd_luts_trivial, ctx->stream);
     launch_ctr_finish(d_st, d_ct, d_out, nb, ctx->stream);
     ctx->launches += 2;
     return check_launch("ctr last round");
@@ -710,7 +725,7 @@ int cbs_lut8_eval(cbs_ctx *ctx, const uint64_t *ggsw_bits, int nbytes, const uin
     TRY(upload(ctx, d_li, li.data(), sizeof(int) * njobs));
     TRY(upload(ctx, d_oi, oi.data(), sizeof(int) * njobs));
     launch_ggsw_to_fourier(ctx->K, d_ggsw, d_ggsw_f, nbits, ctx->stream);
-    launch_lut8(ctx->K, d_ggsw_f, d_luts, d_li, d_oi, d_out, njobs, apb, ctx->stream);
+    launch_lut8(ctx->K, d_ggsw_f, d_luts, d_li, d_oi, d_out, njobs, apb, 0, ctx->stream);
     ctx->launches += 2;
     TRY(check_launch("k_lut8"));
     return download(ctx, out, d_out, (size_t)njobs * 4 * kLweBig * 8);
@@ -764,6 +779,7 @@ int cbs_trans_key_upload(cbs_ctx *ctx, const uint64_t *k10_9, const uint64_t *k8
     TRY(upload(ctx, ctx->d_k8_1, k8_1, (size_t)CBS_K8_1_WORDS * 8));
     TRY(upload(ctx, ctx->d_k0, k0, (size_t)CBS_K0_WORDS * 8));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->inv_luts_trivial = all_masks_zero(k8_1, 8 * 4 * 16 * 2) && all_masks_zero(k0, 16 * 2);
     ctx->have_trans_key = true;
     return CBS_OK;
 }
@@ -804,6 +820,7 @@ int cbs_fwd_trans_key_upload(cbs_ctx *ctx, const uint64_t *kf_first, const uint6
     TRY(upload(ctx, ctx->d_kf_mid, kf_mid, (size_t)CBS_KF_MID_WORDS * 8));
     TRY(upload(ctx, ctx->d_kf_last, kf_last, (size_t)CBS_KF_LAST_WORDS * 8));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->fwd_luts_trivial = all_masks_zero(kf_mid, 8 * 3 * 16 * 2) && all_masks_zero(kf_last, 16 * 2);
     ctx->have_fwd_key = true;
     return CBS_OK;
 }

@@ -1669,17 +1669,175 @@ __global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8(const double *__res
     }
 }
 
+// ---- LUT ladder v2: GGSW row tiles staged through the same 2-deep TMA ring as the blind rotation --------
+// All groups of a CTA evaluate accumulators of the SAME byte, i.e. against the same 8 GGSW bits, so each
+// (level, row) tile of 3 Fourier polynomials is fetched once per CTA.  `groups` = jobs per CTA must divide
+// accs_per_byte (8 -> 4, 6 -> 3, 2 -> 2).  `trivial` = the LUT accumulators are trivial GLWE (zero mask),
+// as every keyed LUT of rounds 8..1 and 0 is (src/data_struct.rs:145-151,258-263): the first CMux then has
+// zero digits for both mask polynomials and 14 of its 21 forward transforms are skipped.
+constexpr int kLut2GroupSmem = kGlweWords * 8 + 2 * 512 * 16;  // 40 KB
+constexpr int kLut2SmemBytes = kLutGroups * kLut2GroupSmem + kBrRing * kBrTileBytes + 1024 + 64;
+
+__global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8_v2(const double *__restrict__ ggsw_f,
+                                                                 const uint64_t *__restrict__ luts,
+                                                                 const int *__restrict__ lut_index,
+                                                                 const int *__restrict__ out_index,
+                                                                 uint64_t *__restrict__ out, int njobs, int accs_per_byte,
+                                                                 const double *__restrict__ twtab, int groups, int trivial)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int job = (gi < groups) ? blockIdx.x * groups + gi : njobs;
+    unsigned char *ring = smem_raw + (size_t)kLutGroups * kLut2GroupSmem;
+    cplx *t2tab = reinterpret_cast<cplx *>(ring + kBrRing * kBrTileBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes + 1024);
+    uint64_t *empty = full + kBrRing;
+    const int active_groups = min(groups, njobs - blockIdx.x * groups);
+    fill_t2_table(t2tab, twtab, threadIdx.x);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kBrRing; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, 64 * active_groups);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (job >= njobs) return;
+    const bool producer = (threadIdx.x == 0);
+    const char *bits = reinterpret_cast<const char *>(ggsw_f + (size_t)((blockIdx.x * groups) / accs_per_byte) * 8 * kGgswWords);
+    constexpr int kTiles = 8 * 21;
+    // tile k = (bit i, row r, digit tt): level 6 - tt, Fourier polys [i][lev][r][0..2]
+    auto tile_src = [&](int k) {
+        const int i = k / 21, r = (k % 21) / 7, lev = 6 - (k % 7);
+        return bits + ((size_t)i * kGgswWords + (size_t)((lev * 3 + r) * 3) * kFourierPolyDoubles) * 8;
+    };
+    if (producer)
+        for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, tile_src(b), kBrTileBytes, full + b);
+
+    unsigned char *base = smem_raw + (size_t)gi * kLut2GroupSmem;
+    uint64_t *acc = reinterpret_cast<uint64_t *>(base);
+    Group g;
+    g.t = threadIdx.x & 63;
+    g.bar = 1 + gi;
+    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    const int t = g.t;
+    const cplx *t2s = t2tab + (t & 7);
+    Twiddles tw;
+    load_twiddles(tw, twtab, t);
+    const uint64_t *src = luts + (size_t)lut_index[job] * kGlweWords;
+    for (int w = t; w < kGlweWords; w += 64) acc[w] = src[w];
+    group_sync(g.bar);
+
+    int tile = 0;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        const int d = 1 << i;
+        cplx o[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) o[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+        for (int r = 0; r < 3; r++) {
+            const bool zero = trivial && i == 0 && r < 2;  // trivial LUT: mask polynomials are exactly zero
+            uint32_t pk[16];
+            if (!zero) {
+                const uint64_t *p = acc + r * 1024;
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const int j = t + 64 * m;
+                    pk[2 * m] = pack_digits<2, 7, uint32_t>(neg_read(p, (j + d) & 2047) - p[j]);  // acc * X^-d - acc
+                    pk[2 * m + 1] = pack_digits<2, 7, uint32_t>(neg_read(p, (j + 512 + d) & 2047) - p[j + 512]);
+                }
+            }
+#pragma unroll 1
+            for (int tt = 0; tt < 7; tt++, tile++) {
+                const int buf = tile % kBrRing, use = tile / kBrRing;
+                if (producer && tile >= 1 && tile - 1 + kBrRing < kTiles) {
+                    const int pb = (tile - 1) % kBrRing, puse = (tile - 1) / kBrRing;
+                    mbar_wait(empty + pb, puse & 1);
+                    tma_load_tile(ring + pb * kBrTileBytes, tile_src(tile - 1 + kBrRing), kBrTileBytes, full + pb);
+                }
+                if (!zero) {
+                    cplx v[8];
+#pragma unroll
+                    for (int m = 0; m < 8; m++)
+                        v[m] = cplx{i32_to_double(unpack_digit<2, uint32_t>(pk[2 * m], tt)),
+                                    i32_to_double(unpack_digit<2, uint32_t>(pk[2 * m + 1], tt))};
+                    cplx *s = g.flip ? g.scr1 : g.scr0;
+                    g.flip ^= 1;
+                    fwd_p1(v, s, tw, t);
+                    group_sync(g.bar);
+                    fwd_p2_s(v, s, t2s, t);
+                    group_sync(g.bar);
+                    mbar_wait(full + buf, use & 1);
+                    const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
+                    cplx kc[8];
+#pragma unroll
+                    for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];
+                    fwd_p3(v, s, t);
+#pragma unroll
+                    for (int k3 = 0; k3 < 8; k3++) cfma(o[0][k3], v[k3], kc[k3]);
+#pragma unroll
+                    for (int c = 1; c < 3; c++)
+#pragma unroll
+                        for (int k3 = 0; k3 < 8; k3++) cfma(o[c][k3], v[k3], key[c * 512 + k3 * 64]);
+                } else {
+                    mbar_wait(full + buf, use & 1);
+                }
+                mbar_arrive(empty + buf);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft_s(o[c], g, tw, t2s);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                acc[c * 1024 + t + 64 * m] += torus_from_scaled(o[c][m].x);
+                acc[c * 1024 + t + 64 * m + 512] += torus_from_scaled(o[c][m].y);
+            }
+        }
+    }
+    group_sync(g.bar);
+    for (int q = 0; q < 4; q++) {
+        const int T = 256 * q;
+        uint64_t *dst = out + (size_t)(out_index[job] + q) * kLweBig;
+        for (int w = t; w < 2048; w += 64) {
+            const int c = w >> 10, j = w & 1023;
+            const uint64_t *mp = acc + c * 1024;
+            dst[w] = (j <= T) ? mp[T - j] : (0ull - mp[1024 + T - j]);
+        }
+        if (t == 0) dst[2048] = acc[2048 + T];
+    }
+}
+
 void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts, const int *lut_index,
-                 const int *out_index, uint64_t *out, int njobs, int accs_per_byte, cudaStream_t s)
+                 const int *out_index, uint64_t *out, int njobs, int accs_per_byte, int trivial, cudaStream_t s)
 {
     if (njobs <= 0) return;
     static bool attr = false;
+    static int variant = 2;
     if (!attr) {
         cudaFuncSetAttribute(k_lut8, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutSmemBytes);
+        cudaFuncSetAttribute(k_lut8_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kLut2SmemBytes);
+        if (const char *e = getenv("CBS_LUT_VARIANT")) variant = atoi(e);
         attr = true;
     }
-    k_lut8<<<(njobs + kLutGroups - 1) / kLutGroups, 64 * kLutGroups, kLutSmemBytes, s>>>(ggsw_f, luts, lut_index, out_index,
-                                                                                          out, njobs, accs_per_byte, K.tw);
+    int groups = 0;
+    for (int gsz = kLutGroups; gsz >= 1; gsz--)
+        if (accs_per_byte % gsz == 0) {
+            groups = gsz;
+            break;
+        }
+    if (variant == 1 || njobs % accs_per_byte != 0)
+        k_lut8<<<(njobs + kLutGroups - 1) / kLutGroups, 64 * kLutGroups, kLutSmemBytes, s>>>(ggsw_f, luts, lut_index,
+                                                                                              out_index, out, njobs,
+                                                                                              accs_per_byte, K.tw);
+    else
+        k_lut8_v2<<<njobs / groups, 64 * kLutGroups, kLut2SmemBytes, s>>>(ggsw_f, luts, lut_index, out_index, out, njobs,
+                                                                          accs_per_byte, K.tw, groups, trivial);
 }
 
 // ------------------------------------------------------------------------------------------------

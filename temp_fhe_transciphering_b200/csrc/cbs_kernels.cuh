@@ -61,8 +61,9 @@ void launch_ggsw_to_fourier(const DeviceKeys &K, const uint64_t *ggsw_std, doubl
 
 // a7  8-bit LUT ladders.  job j: GGSW bits ggsw_f[(j / accs_per_byte) * 8 .. +8], accumulator
 //     lut[lut_index[j]] (GLWE), outputs 4 LWE(2048) written to out[out_index[j] + {0,1,2,3}].
+//     trivial = 1 promises that every accumulator is a trivial GLWE (zero mask polynomials).
 void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts, const int *lut_index,
-                 const int *out_index, uint64_t *out, int njobs, int accs_per_byte, cudaStream_t s);
+                 const int *out_index, uint64_t *out, int njobs, int accs_per_byte, int trivial, cudaStream_t s);
 
 // a8  rounds 10+9: sample extraction from the encrypted keyed LUTs (ct = raw AES ciphertext bytes; the cleartext inv_shift_rows is applied inside)
 //     luts = [nmult][16][2] GLWE, tm = [nmult][nblocks][128][2049]; inv_shift = 1 for the inverse direction
