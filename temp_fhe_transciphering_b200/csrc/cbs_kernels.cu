@@ -1553,6 +1553,123 @@ __global__ void __launch_bounds__(64 * kSsGroups, 1) k_scheme_switch(const uint6
     }
 }
 
+// v2: the 12 scheme-switching-key row tiles go through the 2-deep TMA ring shared by the CTA's groups
+constexpr int kSs2SmemBytes = kSsSmemBytes + kBrRing * kBrTileBytes + 64;
+__global__ void __launch_bounds__(64 * kSsGroups, 1) k_scheme_switch_v2(const uint64_t *__restrict__ glev,
+                                                                      uint64_t *__restrict__ ggsw_std,
+                                                                      double *__restrict__ ggsw_f, int count,
+                                                                      const double *__restrict__ ss_f,
+                                                                      const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int idx = blockIdx.x * kSsGroups + gi;  // (ciphertext, level)
+    // scheme-switching key row tiles (i, level, row) = 3 Fourier polys, shared by the groups of the CTA
+    unsigned char *ring = smem_raw + (size_t)kSsGroups * kSsGroupSmem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes);
+    uint64_t *empty = full + kBrRing;
+    const int active_groups = min(kSsGroups, count * kCbsLevel - blockIdx.x * kSsGroups);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kBrRing; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, 64 * active_groups);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (idx >= count * kCbsLevel) return;
+    const bool producer = (threadIdx.x == 0);
+    constexpr int kTiles = 12;  // (i 2) x (row 3) x (digit 2), consumption order
+    auto tile_src = [&](int k) {
+        const int i = k / 6, r = (k % 6) / 2, lev = 1 - (k % 2);
+        return reinterpret_cast<const char *>(ss_f) + (size_t)(((i * 2 + lev) * 3 + r) * 3) * kFourierPolyDoubles * 8;
+    };
+    if (producer)
+        for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, tile_src(b), kBrTileBytes, full + b);
+    int tile = 0;
+    unsigned char *base = smem_raw + (size_t)gi * kSsGroupSmem;
+    uint64_t *gl = reinterpret_cast<uint64_t *>(base);
+    Group g;
+    g.t = threadIdx.x & 63;
+    g.bar = 1 + gi;
+    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
+    const int t = g.t;
+    const uint64_t *src = glev + (size_t)idx * kGlweWords;
+    for (int w = t; w < kGlweWords; w += 64) gl[w] = src[w];
+    group_sync(g.bar);
+    // GGSW layout [level][row][poly]; idx = ct*7 + level
+    uint64_t *std_base = ggsw_std ? ggsw_std + (size_t)idx * 3 * kGlweWords : nullptr;
+    double *f_base = ggsw_f ? ggsw_f + (size_t)idx * 9 * kFourierPolyDoubles : nullptr;
+
+#pragma unroll 1
+    for (int i = 0; i < 2; i++) {
+        cplx acc[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+        for (int r = 0; r < 3; r++) {
+            uint64_t pk[16];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                pk[2 * m] = pack_digits<17, 2, uint64_t>(gl[r * 1024 + t + 64 * m]);
+                pk[2 * m + 1] = pack_digits<17, 2, uint64_t>(gl[r * 1024 + t + 64 * m + 512]);
+            }
+#pragma unroll 1
+            for (int tt = 0; tt < 2; tt++, tile++) {
+                const int buf = tile % kBrRing, use = tile / kBrRing;
+                if (producer && tile >= 1 && tile - 1 + kBrRing < kTiles) {
+                    const int pb = (tile - 1) % kBrRing, puse = (tile - 1) / kBrRing;
+                    mbar_wait(empty + pb, puse & 1);
+                    tma_load_tile(ring + pb * kBrTileBytes, tile_src(tile - 1 + kBrRing), kBrTileBytes, full + pb);
+                }
+                cplx v[8];
+#pragma unroll
+                for (int m = 0; m < 8; m++)
+                    v[m] = cplx{i32_to_double(unpack_digit<17, uint64_t>(pk[2 * m], tt)),
+                                i32_to_double(unpack_digit<17, uint64_t>(pk[2 * m + 1], tt))};
+                fwd_fft(v, g, tw);
+                mbar_wait(full + buf, use & 1);
+                const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int k3 = 0; k3 < 8; k3++) cfma(acc[c][k3], v[k3], key[c * 512 + k3 * 64]);
+                mbar_arrive(empty + buf);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft(acc[c], g, tw);
+            uint64_t lo[8], hi[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                lo[m] = torus_from_scaled(acc[c][m].x);
+                hi[m] = torus_from_scaled(acc[c][m].y);
+            }
+            emit_row_poly(lo, hi, std_base ? std_base + (size_t)(i * 3 + c) * 1024 : nullptr,
+                          f_base ? f_base + (size_t)(i * 3 + c) * kFourierPolyDoubles : nullptr, g, tw);
+        }
+    }
+    // row k = the GLEV level itself (ggsw_conv.rs:191)
+#pragma unroll 1
+    for (int c = 0; c < 3; c++) {
+        uint64_t lo[8], hi[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            lo[m] = gl[c * 1024 + t + 64 * m];
+            hi[m] = gl[c * 1024 + t + 64 * m + 512];
+        }
+        emit_row_poly(lo, hi, std_base ? std_base + (size_t)(6 + c) * 1024 : nullptr,
+                      f_base ? f_base + (size_t)(6 + c) * kFourierPolyDoubles : nullptr, g, tw);
+    }
+}
+
 void launch_scheme_switch(const DeviceKeys &K, const uint64_t *glev, uint64_t *ggsw_std, double *ggsw_f, int count,
                           cudaStream_t s)
 {
@@ -1560,11 +1677,21 @@ void launch_scheme_switch(const DeviceKeys &K, const uint64_t *glev, uint64_t *g
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_scheme_switch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemBytes);
+        cudaFuncSetAttribute(k_scheme_switch_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs2SmemBytes);
         attr = true;
     }
     const int groups = count * kCbsLevel;
-    k_scheme_switch<<<(groups + kSsGroups - 1) / kSsGroups, 64 * kSsGroups, kSsSmemBytes, s>>>(glev, ggsw_std, ggsw_f,
-                                                                                                 count, K.ss_f, K.tw);
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("CBS_SS_VARIANT");
+        variant = e ? atoi(e) : 2;
+    }
+    if (variant == 1)
+        k_scheme_switch<<<(groups + kSsGroups - 1) / kSsGroups, 64 * kSsGroups, kSsSmemBytes, s>>>(glev, ggsw_std, ggsw_f,
+                                                                                                     count, K.ss_f, K.tw);
+    else
+        k_scheme_switch_v2<<<(groups + kSsGroups - 1) / kSsGroups, 64 * kSsGroups, kSs2SmemBytes, s>>>(glev, ggsw_std, ggsw_f,
+                                                                                                         count, K.ss_f, K.tw);
 }
 
 void launch_ggsw_to_fourier(const DeviceKeys &K, const uint64_t *ggsw_std, double *ggsw_f, int count, cudaStream_t s)
