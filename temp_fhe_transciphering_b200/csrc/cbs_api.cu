@@ -44,11 +44,19 @@ struct cbs_ctx {
     // every mask word of the round 8..1 / round 0 LUTs is zero (always true for AllRdKeys written by the
     // reference, src/data_struct.rs:145-151,258-263); checked at upload, enables the first-CMux shortcut
     int inv_luts_trivial = 0, fwd_luts_trivial = 0;
-    int jobs24_nblocks = -1;
+    int jobs24_nblocks[5] = {-1, -1, -1, -1, -1};
     std::map<std::string, DevBuf> ws;
     // cached LUT job tables, keyed by block count
-    int jobs_nblocks = -1;
     int chunk_blocks = 64;
+    // Lanes: a chunk is processed as up to kMaxLanes block-aligned parts on separate side streams so that
+    // the second (partial) wave of one part's blind rotation overlaps the trace / scheme switch / LUT
+    // kernels of another part.  lane = -1: work is issued on `stream` with un-prefixed workspaces.
+    static constexpr int kMaxLanes = 4;
+    int lanes = 2;
+    int lane = -1;
+    cudaStream_t side[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+    int jobs_nblocks[kMaxLanes + 1] = {-1, -1, -1, -1, -1};
 };
 
 namespace {
@@ -84,12 +92,15 @@ int check_launch(const char *what)
     return CBS_OK;
 }
 
+// stream the current lane issues on
+inline cudaStream_t S(const cbs_ctx *ctx) { return ctx->lane >= 0 ? ctx->side[ctx->lane] : ctx->stream; }
+
 int ws_get(cbs_ctx *ctx, const char *name, size_t bytes, void **out)
 {
-    DevBuf &b = ctx->ws[name];
+    DevBuf &b = ctx->ws[ctx->lane >= 0 ? std::string("lane") + std::to_string(ctx->lane) + ":" + name : std::string(name)];
     if (b.bytes < bytes) {
         if (b.p) {
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(cudaDeviceSynchronize());
             CUDA_TRY(cudaFree(b.p));
             b.p = nullptr;
             b.bytes = 0;
@@ -160,18 +171,18 @@ int download(cbs_ctx *ctx, void *h, const void *d, size_t bytes)
         if (_rc != CBS_OK) return _rc; \
     } while (0)
 
-// ---- device pipelines (all pointers device, async on ctx->stream) ----
+// ---- device pipelines (all pointers device, async on S(ctx)) ----
 
 int dev_keyswitch(cbs_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, int count)
 {
-    launch_lwe_keyswitch(ctx->K, d_in, d_out, count, ctx->stream);
+    launch_lwe_keyswitch(ctx->K, d_in, d_out, count, S(ctx));
     ctx->launches++;
     return check_launch("k_lwe_keyswitch");
 }
 
 int dev_blind_rotate(cbs_ctx *ctx, const uint64_t *d_in, uint64_t *d_acc, int count)
 {
-    launch_blind_rotate(ctx->K, d_in, d_acc, count, ctx->stream);
+    launch_blind_rotate(ctx->K, d_in, d_acc, count, S(ctx));
     ctx->launches++;
     return check_launch("k_blind_rotate");
 }
@@ -182,7 +193,7 @@ int dev_msb_to_glev(cbs_ctx *ctx, const uint64_t *d_in, uint64_t *d_glev, int co
     uint64_t *d_acc;
     TRY(ws_typed(ctx, "acc", (size_t)count * kGlweWords, &d_acc));
     TRY(dev_blind_rotate(ctx, d_in, d_acc, count));
-    launch_trace(ctx->K, d_acc, d_glev, count * kCbsLevel, 1, ctx->stream);
+    launch_trace(ctx->K, d_acc, d_glev, count * kCbsLevel, 1, S(ctx));
     ctx->launches++;
     return check_launch("k_trace");
 }
@@ -193,7 +204,7 @@ int dev_circuit_bootstrap(cbs_ctx *ctx, const uint64_t *d_in, uint64_t *d_ggsw_s
     uint64_t *d_glev;
     TRY(ws_typed(ctx, "glev", (size_t)count * kGlevWords, &d_glev));
     TRY(dev_msb_to_glev(ctx, d_in, d_glev, count));
-    launch_scheme_switch(ctx->K, d_glev, d_ggsw_std, d_ggsw_f, count, ctx->stream);
+    launch_scheme_switch(ctx->K, d_glev, d_ggsw_std, d_ggsw_f, count, S(ctx));
     ctx->launches++;
     return check_launch("k_scheme_switch");
 }
@@ -205,7 +216,7 @@ int ensure_job_tables(cbs_ctx *ctx, int nb, int **lut32, int **out32, int **lut8
     TRY(ws_typed(ctx, "job_out32", (size_t)j32, out32));
     TRY(ws_typed(ctx, "job_lut8", (size_t)j8, lut8));
     TRY(ws_typed(ctx, "job_out8", (size_t)j8, out8));
-    if (ctx->jobs_nblocks == nb) return CBS_OK;
+    if (ctx->jobs_nblocks[ctx->lane + 1] == nb) return CBS_OK;
     std::vector<int> l32(j32), o32(j32), l8(j8), o8(j8);
     for (int blk = 0; blk < nb; blk++)
         for (int byte = 0; byte < 16; byte++) {
@@ -221,17 +232,17 @@ int ensure_job_tables(cbs_ctx *ctx, int nb, int **lut32, int **out32, int **lut8
                 o8[job] = blk * 128 + byte * 8 + 4 * a;
             }
         }
-    CUDA_TRY(cudaMemcpyAsync(*lut32, l32.data(), sizeof(int) * j32, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(*out32, o32.data(), sizeof(int) * j32, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(*lut8, l8.data(), sizeof(int) * j8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(*out8, o8.data(), sizeof(int) * j8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
-    ctx->jobs_nblocks = nb;
+    CUDA_TRY(cudaMemcpyAsync(*lut32, l32.data(), sizeof(int) * j32, cudaMemcpyHostToDevice, S(ctx)));
+    CUDA_TRY(cudaMemcpyAsync(*out32, o32.data(), sizeof(int) * j32, cudaMemcpyHostToDevice, S(ctx)));
+    CUDA_TRY(cudaMemcpyAsync(*lut8, l8.data(), sizeof(int) * j8, cudaMemcpyHostToDevice, S(ctx)));
+    CUDA_TRY(cudaMemcpyAsync(*out8, o8.data(), sizeof(int) * j8, cudaMemcpyHostToDevice, S(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(S(ctx)));  // host vectors go out of scope
+    ctx->jobs_nblocks[ctx->lane + 1] = nb;
     return CBS_OK;
 }
 
 // aes_to_lwe_trasnciphering for one chunk of nb blocks
-int dev_transcipher_chunk(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d_out)
+int dev_transcipher_part(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d_out)
 {
     const int B = nb * 128;
     uint64_t *d_t4, *d_st, *d_ks;
@@ -243,8 +254,8 @@ int dev_transcipher_chunk(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d
     TRY(ws_typed(ctx, "ggsw_f", (size_t)B * kGgswWords, &d_ggsw_f));
     TRY(ensure_job_tables(ctx, nb, &lut32, &out32, &lut8, &out8));
     // rounds 10 + 9 (server_encrypted_aes_decryption.rs:89-128)
-    launch_known_rotate(d_ct, ctx->d_k10_9, d_t4, nb, 4, 1, ctx->stream);
-    launch_inv_linear(d_t4, d_st, nb, ctx->stream);
+    launch_known_rotate(d_ct, ctx->d_k10_9, d_t4, nb, 4, 1, S(ctx));
+    launch_inv_linear(d_t4, d_st, nb, S(ctx));
     ctx->launches += 2;
     TRY(check_launch("first rounds"));
     // rounds 8..1 (:130-163)
@@ -252,22 +263,22 @@ int dev_transcipher_chunk(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d
         TRY(dev_keyswitch(ctx, d_st, d_ks, B));
         TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
         const uint64_t *luts = ctx->d_k8_1 + (size_t)(round - 1) * 4 * 16 * 2 * kGlweWords;
-        launch_lut8(ctx->K, d_ggsw_f, luts, lut32, out32, d_t4, nb * 16 * 8, 8, ctx->inv_luts_trivial, ctx->stream);
-        launch_inv_linear(d_t4, d_st, nb, ctx->stream);
+        launch_lut8(ctx->K, d_ggsw_f, luts, lut32, out32, d_t4, nb * 16 * 8, 8, ctx->inv_luts_trivial, S(ctx));
+        launch_inv_linear(d_t4, d_st, nb, S(ctx));
         ctx->launches += 2;
         TRY(check_launch("round"));
     }
     // last round (:166-180) + per-byte bit reversal (:182-189)
     TRY(dev_keyswitch(ctx, d_st, d_ks, B));
     TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
-    launch_lut8(ctx->K, d_ggsw_f, ctx->d_k0, lut8, out8, d_st, nb * 16 * 2, 2, ctx->inv_luts_trivial, ctx->stream);
-    launch_reverse_bits(d_st, d_out, nb, ctx->stream);
+    launch_lut8(ctx->K, d_ggsw_f, ctx->d_k0, lut8, out8, d_st, nb * 16 * 2, 2, ctx->inv_luts_trivial, S(ctx));
+    launch_reverse_bits(d_st, d_out, nb, S(ctx));
     ctx->launches += 2;
     return check_launch("last round");
 }
 
 // CTR mode: forward AES of the public counter blocks (aes_he.rs:285-474), one chunk of nb blocks
-int dev_ctr_chunk(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int nb, uint64_t *d_out)
+int dev_ctr_part(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int nb, uint64_t *d_out)
 {
     const int B = nb * 128;
     uint64_t *d_t3, *d_st, *d_ks;
@@ -281,7 +292,7 @@ int dev_ctr_chunk(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int n
     const int j24 = nb * 16 * 6;
     TRY(ws_typed(ctx, "job_lut24", (size_t)j24, &lut24));
     TRY(ws_typed(ctx, "job_out24", (size_t)j24, &out24));
-    if (ctx->jobs24_nblocks != nb) {
+    if (ctx->jobs24_nblocks[ctx->lane + 1] != nb) {
         std::vector<int> l(j24), o(j24);
         for (int blk = 0; blk < nb; blk++)
             for (int byte = 0; byte < 16; byte++)
@@ -291,31 +302,67 @@ int dev_ctr_chunk(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int n
                         l[job] = (m * 16 + byte) * 2 + a;
                         o[job] = (m * nb + blk) * 128 + byte * 8 + 4 * a;
                     }
-        CUDA_TRY(cudaMemcpyAsync(lut24, l.data(), sizeof(int) * j24, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(out24, o.data(), sizeof(int) * j24, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        ctx->jobs24_nblocks = nb;
+        CUDA_TRY(cudaMemcpyAsync(lut24, l.data(), sizeof(int) * j24, cudaMemcpyHostToDevice, S(ctx)));
+        CUDA_TRY(cudaMemcpyAsync(out24, o.data(), sizeof(int) * j24, cudaMemcpyHostToDevice, S(ctx)));
+        CUDA_TRY(cudaStreamSynchronize(S(ctx)));
+        ctx->jobs24_nblocks[ctx->lane + 1] = nb;
     }
     // round 1: the counter block is public -> keyed LUTs are "rotated" by sample extraction
-    launch_known_rotate(d_ctr, ctx->d_kf_first, d_t3, nb, 3, 0, ctx->stream);
-    launch_fwd_linear(d_t3, d_st, nb, ctx->stream);
+    launch_known_rotate(d_ctr, ctx->d_kf_first, d_t3, nb, 3, 0, S(ctx));
+    launch_fwd_linear(d_t3, d_st, nb, S(ctx));
     ctx->launches += 2;
     TRY(check_launch("ctr round 1"));
     for (int round = 2; round <= 9; round++) {
         TRY(dev_keyswitch(ctx, d_st, d_ks, B));
         TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
         const uint64_t *luts = ctx->d_kf_mid + (size_t)(round - 2) * 3 * 16 * 2 * kGlweWords;
-        launch_lut8(ctx->K, d_ggsw_f, luts, lut24, out24, d_t3, j24, 6, ctx->fwd_luts_trivial, ctx->stream);
-        launch_fwd_linear(d_t3, d_st, nb, ctx->stream);
+        launch_lut8(ctx->K, d_ggsw_f, luts, lut24, out24, d_t3, j24, 6, ctx->fwd_luts_trivial, S(ctx));
+        launch_fwd_linear(d_t3, d_st, nb, S(ctx));
         ctx->launches += 2;
         TRY(check_launch("ctr round"));
     }
     TRY(dev_keyswitch(ctx, d_st, d_ks, B));
     TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
-    launch_lut8(ctx->K, d_ggsw_f, ctx->d_kf_last, lut8, out8, d_st, nb * 16 * 2, 2, ctx->fwd_luts_trivial, ctx->stream);
-    launch_ctr_finish(d_st, d_ct, d_out, nb, ctx->stream);
+    launch_lut8(ctx->K, d_ggsw_f, ctx->d_kf_last, lut8, out8, d_st, nb * 16 * 2, 2, ctx->fwd_luts_trivial, S(ctx));
+    launch_ctr_finish(d_st, d_ct, d_out, nb, S(ctx));
     ctx->launches += 2;
     return check_launch("ctr last round");
+}
+
+// Run `part(lane_index, first_block, block_count)` over a chunk split into block-aligned lanes on the side
+// streams, forked from and joined back into ctx->stream with events (no host synchronisation).
+template <typename Fn>
+int run_in_lanes(cbs_ctx *ctx, int nb, Fn part)
+{
+    const int P = std::max(1, std::min(std::min(ctx->lanes, (int)cbs_ctx::kMaxLanes), nb));
+    if (P == 1) return part(0, nb);
+    CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    int rc = CBS_OK;
+    for (int l = 0; l < P && rc == CBS_OK; l++) {
+        const int b0 = (int)((long)nb * l / P), b1 = (int)((long)nb * (l + 1) / P);
+        CUDA_TRY(cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
+        ctx->lane = l;
+        rc = part(b0, b1 - b0);
+        ctx->lane = -1;
+        if (rc != CBS_OK) break;
+        CUDA_TRY(cudaEventRecord(ctx->ev_join[l], ctx->side[l]));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
+    }
+    return rc;
+}
+
+int dev_transcipher_chunk(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d_out)
+{
+    return run_in_lanes(ctx, nb, [&](int b0, int n) {
+        return dev_transcipher_part(ctx, d_ct + (size_t)b0 * 16, n, d_out + (size_t)b0 * 128 * kLweBig);
+    });
+}
+
+int dev_ctr_chunk(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int nb, uint64_t *d_out)
+{
+    return run_in_lanes(ctx, nb, [&](int b0, int n) {
+        return dev_ctr_part(ctx, d_ctr + (size_t)b0 * 16, d_ct + (size_t)b0 * 16, n, d_out + (size_t)b0 * 128 * kLweBig);
+    });
 }
 
 int dev_ctr(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int nblocks, uint64_t *d_out)
@@ -386,6 +433,7 @@ int cbs_ctx_create(const cbs_keyset *ks, int device, cbs_ctx **out)
     auto *ctx = new cbs_ctx;
     ctx->device = device;
     if (const char *e = getenv("CBS_CHUNK_BLOCKS")) ctx->chunk_blocks = std::max(1, atoi(e));
+    if (const char *e = getenv("CBS_LANES")) ctx->lanes = std::max(1, std::min((int)cbs_ctx::kMaxLanes, atoi(e)));
     Activate act(ctx);
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -397,6 +445,17 @@ int cbs_ctx_create(const cbs_keyset *ks, int device, cbs_ctx **out)
         cbs_ctx_destroy(ctx);
         return rc;
     };
+    for (int l = 0; l < cbs_ctx::kMaxLanes; l++) {
+        if (cudaStreamCreateWithFlags(&ctx->side[l], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming) != cudaSuccess) {
+            set_error("cannot create lane streams");
+            return fail(CBS_ERR_CUDA);
+        }
+    }
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("cannot create lane events");
+        return fail(CBS_ERR_CUDA);
+    }
     // twiddle tables
     std::vector<double> tw = make_twiddle_table();
     std::vector<double> tw128(256 + 128);
@@ -490,6 +549,7 @@ void cbs_ctx_destroy(cbs_ctx *ctx)
     if (!ctx) return;
     Activate act(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     for (void *p : ctx->key_allocs) cudaFree(p);
     for (auto &kv : ctx->ws)
         if (kv.second.p) cudaFree(kv.second.p);
@@ -499,6 +559,11 @@ void cbs_ctx_destroy(cbs_ctx *ctx)
     if (ctx->d_kf_first) cudaFree(ctx->d_kf_first);
     if (ctx->d_kf_mid) cudaFree(ctx->d_kf_mid);
     if (ctx->d_kf_last) cudaFree(ctx->d_kf_last);
+    for (int l = 0; l < cbs_ctx::kMaxLanes; l++) {
+        if (ctx->side[l]) cudaStreamDestroy(ctx->side[l]);
+        if (ctx->ev_join[l]) cudaEventDestroy(ctx->ev_join[l]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -291,7 +291,10 @@ __global__ void __launch_bounds__(kKsThreads) k_lwe_keyswitch(const uint64_t *__
 void launch_lwe_keyswitch(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int count, cudaStream_t s)
 {
     if (count <= 0) return;
-    static bool attr = false;
+    static bool attr_done[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool &attr = attr_done[attr_dev & 63];
     if (!attr) {
         cudaFuncSetAttribute(k_lwe_keyswitch, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsSmemBytes);
         attr = true;
@@ -845,7 +848,10 @@ static int br_variant()
 void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc, int count, cudaStream_t s)
 {
     if (count <= 0) return;
-    static bool attr = false;
+    static bool attr_done[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool &attr = attr_done[attr_dev & 63];
     if (!attr) {
         cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrTmaSmemBytes);
@@ -1406,7 +1412,10 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
 void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int count, int from_acc, cudaStream_t s)
 {
     if (count <= 0) return;
-    static bool init = false;
+    static bool init_done[64] = {false};
+    int init_dev = 0;
+    cudaGetDevice(&init_dev);
+    bool &init = init_done[init_dev & 63];
     if (!init) {
         int kinv[10];
         for (int i = 0; i < 10; i++) {
@@ -1674,7 +1683,10 @@ void launch_scheme_switch(const DeviceKeys &K, const uint64_t *glev, uint64_t *g
                           cudaStream_t s)
 {
     if (count <= 0) return;
-    static bool attr = false;
+    static bool attr_done[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool &attr = attr_done[attr_dev & 63];
     if (!attr) {
         cudaFuncSetAttribute(k_scheme_switch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemBytes);
         cudaFuncSetAttribute(k_scheme_switch_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs2SmemBytes);
@@ -1944,7 +1956,10 @@ void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts
                  const int *out_index, uint64_t *out, int njobs, int accs_per_byte, int trivial, cudaStream_t s)
 {
     if (njobs <= 0) return;
-    static bool attr = false;
+    static bool attr_done[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool &attr = attr_done[attr_dev & 63];
     static int variant = 2;
     if (!attr) {
         cudaFuncSetAttribute(k_lut8, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutSmemBytes);
@@ -2187,7 +2202,10 @@ void launch_max_ladder(const DeviceKeys &K, const double *ggsw_f, const uint64_t
                        const int *b_idx, uint64_t *out, int npairs, cudaStream_t s)
 {
     if (npairs <= 0) return;
-    static bool attr = false;
+    static bool attr_done[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool &attr = attr_done[attr_dev & 63];
     if (!attr) {
         cudaFuncSetAttribute(k_max_ladder, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
         attr = true;
