@@ -404,8 +404,9 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate(const uint64
     for (int j = t; j < kGlweWords; j += 64) o[j] = acc[j];
 }
 
-// ---- TMA-staged variant -----------------------------------------------------------------------------
-// The 4 groups of a CTA consume the same BSK tiles (BSK_i row r = 3 Fourier polys = 24,576 B) in the
+// ---- key tiles through a bulk-copy (TMA) ring ------------------------------------------------------------
+// Used by the blind rotation, the trace, the scheme switch and the LUT ladders.  Described for the blind
+// rotation: the 4 groups of a CTA consume the same BSK tiles (BSK_i row r = 3 Fourier polys = 24,576 B) in the
 // same order, so each tile is fetched ONCE per CTA with a bulk asynchronous copy (cp.async.bulk, the
 // 1-D TMA path: SASS UBLKCP) into a 2-deep shared-memory ring guarded by full/empty mbarriers, while
 // the groups are still busy with the forward FFT that precedes its use.  This removes the exposed
@@ -414,7 +415,6 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate(const uint64
 // releases a tile with one mbarrier arrive after its last read, so no extra group barrier is needed.
 constexpr int kBrTileBytes = 3 * 512 * 16;  // 24,576
 constexpr int kBrRing = 2;
-constexpr int kBrTmaSmemBytes = kBrGroups * kBrGroupSmem + kBrRing * kBrTileBytes + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -447,122 +447,6 @@ __device__ __forceinline__ void tma_load_tile(void *dst, const void *src, uint32
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-
-__global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_tma(const uint64_t *__restrict__ lwe,
-                                                                         uint64_t *__restrict__ acc_out, int count,
-                                                                         const double *__restrict__ bsk_f,
-                                                                         const double *__restrict__ twtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6;
-    const int ct = blockIdx.x * kBrGroups + gi;
-    unsigned char *ring = smem_raw + (size_t)kBrGroups * kBrGroupSmem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes);
-    uint64_t *empty = full + kBrRing;
-    const int active_groups = min(kBrGroups, count - blockIdx.x * kBrGroups);
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < kBrRing; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, 64 * active_groups);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (ct >= count) return;
-    const bool producer = (threadIdx.x == 0);
-    const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
-    constexpr int kTiles = kLweN * 3;
-    if (producer)
-        for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
-
-    unsigned char *base = smem_raw + (size_t)gi * kBrGroupSmem;
-    uint64_t *acc = reinterpret_cast<uint64_t *>(base);
-    Group g;
-    g.t = threadIdx.x & 63;
-    g.bar = 1 + gi;
-    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
-    g.scr1 = g.scr0 + 512;
-    g.flip = 0;
-    Twiddles tw;
-    load_twiddles(tw, twtab, g.t);
-    const uint64_t *a = lwe + (size_t)ct * kLweSmall;
-    const int t = g.t;
-    {
-        const int bt = modswitch_dev(a[kLweN]);
-        for (int j = t; j < 1024; j += 64) {
-            acc[j] = 0;
-            acc[1024 + j] = 0;
-            const int e = (j + bt) & 2047;
-            const int i = e & 1023;
-            uint64_t val = 1ull << (61 - 2 * (i & 7));
-            const bool neg = (i < 512) != ((e & 1024) != 0);
-            acc[2048 + j] = neg ? (0ull - val) : val;
-        }
-    }
-    group_sync(g.bar);
-
-    int tile = 0;
-#pragma unroll 1
-    for (int i = 0; i < kLweN; i++) {
-        const int d = modswitch_dev(__ldg(a + i)) & 2047;
-        const bool skip = (d == 0);  // ct1 == 0: nothing to add, but the tiles are still consumed
-        cplx out[3][8];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
-#pragma unroll 1
-        for (int r = 0; r < 3; r++, tile++) {
-            const int buf = tile % kBrRing;
-            const int use = tile / kBrRing;
-            // refill the buffer that tile-1 occupied with tile-1+ring, once every group released it
-            if (producer && tile >= 1 && tile - 1 + kBrRing < kTiles) {
-                const int pb = (tile - 1) % kBrRing, puse = (tile - 1) / kBrRing;
-                mbar_wait(empty + pb, puse & 1);
-                tma_load_tile(ring + pb * kBrTileBytes, bsk_bytes + (size_t)(tile - 1 + kBrRing) * kBrTileBytes, kBrTileBytes,
-                              full + pb);
-            }
-            cplx v[8];
-            if (!skip) {
-                const uint64_t *p = acc + r * 1024;
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const int j = t + 64 * m;
-                    const int e = (j - d) & 2047;
-                    uint64_t xl = neg_read(p, e) - p[j];
-                    uint64_t xh = neg_read(p, (e + 512) & 2047) - p[j + 512];
-                    uint64_t sl = decomp_init(xl, 23, 1), sh = decomp_init(xh, 23, 1);
-                    v[m] = cplx{i32_to_double(decomp_next(sl, 23)), i32_to_double(decomp_next(sh, 23))};
-                }
-                fwd_fft(v, g, tw);
-            }
-            mbar_wait(full + buf, use & 1);
-            if (!skip) {
-                const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes);
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-#pragma unroll
-                    for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[c * 512 + k3 * 64 + t]);
-            }
-            mbar_arrive(empty + buf);
-        }
-        if (skip) continue;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            inv_fft(out[c], g, tw);
-            uint64_t *p = acc + c * 1024;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int j = t + 64 * m;
-                p[j] += torus_from_scaled(out[c][m].x);
-                p[j + 512] += torus_from_scaled(out[c][m].y);
-            }
-        }
-    }
-    group_sync(g.bar);
-    uint64_t *o = acc_out + (size_t)ct * kGlweWords;
-    for (int j = t; j < kGlweWords; j += 64) o[j] = acc[j];
 }
 
 // ---- v3: TMA-staged + instruction diet --------------------------------------------------------------
@@ -839,7 +723,7 @@ static int br_variant()
 {
     static int v = -1;
     if (v < 0) {
-        const char *e = getenv("CBS_BR_VARIANT");  // 0 = LDG keys, 1 = TMA ring, 2 = TMA ring + v3 (default)
+        const char *e = getenv("CBS_BR_VARIANT");  // 0 = keys by coalesced LDG (first version, kept for A/B runs), otherwise the TMA-ring kernel (default)
         v = e ? atoi(e) : 2;
     }
     return v;
@@ -854,7 +738,6 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     bool &attr = attr_done[attr_dev & 63];
     if (!attr) {
         cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrTmaSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         attr = true;
@@ -862,8 +745,6 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     const int grid = (count + kBrGroups - 1) / kBrGroups;
     if (br_variant() == 0)
         k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-    else if (br_variant() == 1)
-        k_blind_rotate_tma<<<grid, 64 * kBrGroups, kBrTmaSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
     else {
         static int split = -1, sms = 0;
         if (split < 0) {
@@ -932,102 +813,7 @@ void launch_glev_from_acc(const uint64_t *acc, uint64_t *glev, int count, cudaSt
 // ------------------------------------------------------------------------------------------------
 // K4: trace_assign, cbs_lib/src/automorphism.rs:195-233: 10 x [X -> X^kappa (utils.rs:475-490),
 // keyswitch_glwe_ciphertext with Split(41) two-limb FFT (fourier_glwe_keyswitch.rs:213-342), add].
-constexpr int kTrGroups = 3;
-constexpr int kTrGroupSmem = 2 * kGlweWords * 8 + 2 * 512 * 16;  // cur + nxt + 2 tiles = 64 KB
-constexpr int kTrSmemBytes = kTrGroups * kTrGroupSmem;
 __constant__ int c_kappa_inv[10];  // kappa^-1 mod 2048 for kappa = (1024 >> s) + 1
-
-__global__ void __launch_bounds__(64 * kTrGroups, 1) k_trace(const uint64_t *__restrict__ in,
-                                                              uint64_t *__restrict__ out, int count, int from_acc,
-                                                              const double *__restrict__ auto_f,
-                                                              const double *__restrict__ twtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6;
-    const int idx = blockIdx.x * kTrGroups + gi;
-    if (idx >= count) return;
-    unsigned char *base = smem_raw + (size_t)gi * kTrGroupSmem;
-    uint64_t *cur = reinterpret_cast<uint64_t *>(base);
-    uint64_t *nxt = cur + kGlweWords;
-    Group g;
-    g.t = threadIdx.x & 63;
-    g.bar = 1 + gi;
-    g.scr0 = reinterpret_cast<cplx *>(base + 2 * kGlweWords * 8);
-    g.scr1 = g.scr0 + 512;
-    g.flip = 0;
-    Twiddles tw;
-    load_twiddles(tw, twtab, g.t);
-    const int t = g.t;
-
-    if (from_acc) {
-        const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
-        const int lvl = idx % kCbsLevel;
-        for (int w = t; w < kGlweWords; w += 64) cur[w] = glev_pre_word(acc, lvl, w >> 10, w & 1023);
-    } else {
-        const uint64_t *src = in + (size_t)idx * kGlweWords;
-        for (int w = t; w < kGlweWords; w += 64) cur[w] = src[w];
-    }
-    group_sync(g.bar);
-
-#pragma unroll 1
-    for (int s = 0; s < 10; s++) {
-        const int kinv = c_kappa_inv[s];
-        // nxt = cur + (0, 0, body(X^kappa))   (keyswitch output starts as (0, .., 0, body))
-        for (int m = 0; m < 16; m++) {
-            const int j = t + 64 * m;
-            nxt[j] = cur[j];
-            nxt[1024 + j] = cur[1024 + j];
-            nxt[2048 + j] = cur[2048 + j] + neg_read(cur + 2048, (j * kinv) & 2047);
-        }
-#pragma unroll 1
-        for (int sp = 0; sp < 2; sp++) {
-            cplx acc[3][8];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
-#pragma unroll 1
-            for (int i = 0; i < 2; i++) {
-                uint64_t pk[16];
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const int j = t + 64 * m;
-                    pk[2 * m] = pack_digits<13, 3, uint64_t>(neg_read(cur + i * 1024, (j * kinv) & 2047));
-                    pk[2 * m + 1] = pack_digits<13, 3, uint64_t>(neg_read(cur + i * 1024, ((j + 512) * kinv) & 2047));
-                }
-#pragma unroll 1
-                for (int tt = 0; tt < 3; tt++) {
-                    const int lev = 2 - tt;
-                    cplx v[8];
-#pragma unroll
-                    for (int m = 0; m < 8; m++)
-                        v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m], tt)),
-                                    i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m + 1], tt))};
-                    fwd_fft(v, g, tw);
-                    const double *key = auto_f + (size_t)((((s * 2 + i) * 2 + sp) * 3 + lev) * 3) * kFourierPolyDoubles;
-                    mul_acc<3>(acc, v, key, t);
-                }
-            }
-            const int shift = sp ? 41 : 0;  // fourier_glwe_keyswitch.rs:334-339
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                inv_fft(acc[c], g, tw);
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const int j = t + 64 * m;
-                    nxt[c * 1024 + j] += torus_from_scaled(acc[c][m].x) << shift;
-                    nxt[c * 1024 + j + 512] += torus_from_scaled(acc[c][m].y) << shift;
-                }
-            }
-        }
-        group_sync(g.bar);
-        uint64_t *tmp = cur;
-        cur = nxt;
-        nxt = tmp;
-    }
-    uint64_t *dst = out + (size_t)idx * kGlweWords;
-    for (int w = t; w < kGlweWords; w += 64) dst[w] = cur[w];
-}
 
 // ---- trace v2: both key limbs in one pass, two cooperating 64-thread sub-groups per GLWE ----------------
 // The Split(41) keyswitch needs Sum_F F x K_lo and Sum_F F x K_hi over the same six digit spectra F.
@@ -1426,7 +1212,6 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
             kinv[i] = x;
         }
         cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
-        cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmemBytes);
         cudaFuncSetAttribute(k_trace_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr2SmemBytes);
         cudaFuncSetAttribute(k_trace_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
         init = true;
@@ -1439,9 +1224,6 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
     if (variant == 3)
         k_trace_v3<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
                                                                                                K.auto_f, K.tw);
-    else if (variant == 1)
-        k_trace<<<(count + kTrGroups - 1) / kTrGroups, 64 * kTrGroups, kTrSmemBytes, s>>>(in, out, count, from_acc, K.auto_f,
-                                                                                           K.tw);
     else
         k_trace_v2<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr2SmemBytes, s>>>(in, out, count, from_acc,
                                                                                                K.auto_f, K.tw);
