@@ -714,6 +714,8 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
 //   * five groups per CTA with a single transpose tile: ptxas caps 320 threads at 168 registers, 472 B of
 //     spills: 23.6 ms;
 //   * three polynomials in flight per group with 3 groups per CTA (ILP instead of occupancy): 18.5 ms;
+//   * polynomials 0,1 and columns 0,1 transformed as pairs between the same barriers (2x ILP, same
+//     occupancy): 13.7 ms, 136 B of spills;
 //   * pass-2 twiddles in a shared table: 13.3 ms; balancing the last wave with 3-group CTAs: -2 % only,
 //     because a group's step is a latency chain that does not speed up when its neighbours leave.
 // Per-step cycle budget of a v3 group (CBS_BR_PROF=1): build 4.2 k, forward passes 3.3 k, pass 3 + MAC 2.8 k,
