@@ -110,6 +110,11 @@ int cbs_lwe_list_load(const char *path, uint64_t **data /* malloc'd, free with c
                       uint64_t *lwe_words);
 int cbs_lwe_list_save(const char *path, const uint64_t *data, uint64_t count, uint64_t lwe_words);
 void cbs_free(void *p);
+/* client side: decrypt_decode_lwe_list (submission/src/help_fun.rs:12-42), delta = 2^63; sk has n words */
+int cbs_lwe_decrypt_bits(const uint64_t *sk, int n, const uint64_t *lwe, uint64_t count, uint64_t *bits_out);
+/* bincode Vec<u64>: io/<s>/intermediate/decoded_result{,_aes}.txt */
+int cbs_u64_vec_save(const char *path, const uint64_t *data, uint64_t n);
+int cbs_u64_vec_load(const char *path, uint64_t **data /* free with cbs_free */, uint64_t *n);
 /* encrypt bits (0/1) at delta = 2^63 under the big LWE key (tests / microbench inputs) */
 int cbs_encrypt_bits_big(const cbs_keyset *ks, const uint8_t *bits, int count, uint64_t seed, uint64_t *out);
 /* ... and under the small (768) key, input format of the blind rotation */

@@ -996,6 +996,57 @@ int cbs_lwe_list_save(const char *path, const uint64_t *data, uint64_t count, ui
     return CBS_OK;
 }
 
+// decrypt_decode_lwe_list / decrypt, submission/src/help_fun.rs:12-42 (delta = 2^63)
+int cbs_lwe_decrypt_bits(const uint64_t *sk, int n, const uint64_t *lwe, uint64_t count, uint64_t *bits_out)
+{
+    if (!sk || !lwe || !bits_out || n <= 0) return CBS_ERR_ARG;
+    const uint64_t delta = 1ull << 63;
+    for (uint64_t c = 0; c < count; c++) {
+        const uint64_t *ct = lwe + c * (uint64_t)(n + 1);
+        uint64_t phase = ct[n];
+        for (int i = 0; i < n; i++)
+            if (sk[i]) phase -= ct[i];
+        const uint64_t rounding = (phase & (delta >> 1)) << 1;
+        bits_out[c] = (phase + rounding) / delta;
+    }
+    return CBS_OK;
+}
+
+// bincode Vec<u64> (the intermediate/decoded_result*.txt files of the client stages)
+int cbs_u64_vec_save(const char *path, const uint64_t *data, uint64_t n)
+{
+    if (!path || (!data && n)) return CBS_ERR_ARG;
+    Writer w;
+    w.vec(data, n);
+    std::string p(path);
+    size_t slash = p.find_last_of('/');
+    if (slash != std::string::npos) mkdirs(p.substr(0, slash));
+    if (!w.save(p)) {
+        set_error("cannot write " + p);
+        return CBS_ERR_IO;
+    }
+    return CBS_OK;
+}
+
+int cbs_u64_vec_load(const char *path, uint64_t **data, uint64_t *n)
+{
+    Reader r;
+    if (!path || !data || !n || !r.load(path)) {
+        set_error(std::string("cannot read ") + (path ? path : "(null)"));
+        return CBS_ERR_IO;
+    }
+    uint64_t len = r.u64();
+    if (!r.ok || r.off + 8 * len != r.buf.size()) {
+        set_error(std::string(path) + ": not a bincode Vec<u64>");
+        return CBS_ERR_FORMAT;
+    }
+    uint64_t *p = (uint64_t *)malloc(8 * (len ? len : 1));
+    memcpy(p, r.buf.data() + r.off, 8 * len);
+    *data = p;
+    *n = len;
+    return CBS_OK;
+}
+
 static int encrypt_bits(const uint64_t *sk, int n, double std, const uint8_t *bits, int count, uint64_t seed, uint64_t *out)
 {
     for (int c = 0; c < count; c++) {

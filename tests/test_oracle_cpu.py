@@ -250,3 +250,31 @@ def test_stage_binary_cli_contract(cbs, tmp_path):
     assert r.returncode == 1 and "Usage:" in r.stderr
     r = subprocess.run([exe, "0"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode != 0  # missing datasets/toy/db.hex -> error, like the reference's `?`
+
+
+def test_client_stage_tools_match_reference_clients(cbs, keyset, tmp_path):
+    """Our C++ client_decrypt_decode* / client_postprocess* against the reference's prebuilt binaries on the
+    same files (byte-identical intermediate and result files)."""
+    import aes_clear
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    ours = os.path.join(ROOT, "temp_fhe_transciphering_b200", "bin")
+    vals = [513, 65535, 0, 40000, 7, 12345, 1, 60000]
+    bits = np.array([(v >> (15 - i)) & 1 for v in vals for i in range(16)], dtype=np.uint8)
+    lwe = keyset.encrypt_bits_big(bits, 5)
+    outs = {}
+    for name, bindir in (("ours", ours), ("ref", ref)):
+        if not os.path.exists(os.path.join(bindir, "client_decrypt_decode")):
+            continue
+        d = tmp_path / name
+        keyset.save_dir(d / "io" / "toy", with_secret=True)
+        cbs.save_lwe_list(d / "io" / "toy" / "ciphertext_aes_download" / "result.bin", lwe)
+        cbs.save_lwe_list(d / "io" / "toy" / "ciphertexts_download" / "result.bin", lwe[:16])
+        for exe in ("client_decrypt_decode_aes_decryption", "client_postprocess_aes_decryption",
+                    "client_decrypt_decode", "client_postprocess"):
+            subprocess.run([os.path.join(bindir, exe), "0"], cwd=d, check=True)
+        outs[name] = {f: (d / "io" / "toy" / f).read_bytes() for f in
+                      ("intermediate/decoded_result_aes.txt", "intermediate/decoded_result.txt", "result_aes.txt", "result.txt")}
+    assert outs["ours"]["result_aes.txt"].decode().split() == [str(v) for v in vals]
+    assert outs["ours"]["result.txt"].decode().split() == [str(vals[0])]
+    if "ref" in outs:
+        assert outs["ours"] == outs["ref"]

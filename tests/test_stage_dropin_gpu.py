@@ -80,3 +80,23 @@ def test_small_instance_ctr_mode(tmp_path):
     got_max = [int(x) for x in (d / "io" / "small" / "result.txt").read_text().split()]
     assert got == vals
     assert got_max == [max(vals)]
+
+
+def test_all_ten_stages_ours(tmp_path):
+    """The whole stage sequence of harness/run_submission.py:69-115 with OUR executables only (seeded
+    client stages in C++, GPU server stages), toy instance / ECB."""
+    import aes_clear
+    rng = np.random.default_rng(77)
+    vals = rng.integers(0, 65536, 8).tolist()
+    key = aes_clear.harness_aes_key(None)
+    d = tmp_path
+    os.makedirs(d / "datasets" / "toy")
+    (d / "datasets" / "toy" / "aes_key.hex").write_text(key.hex())
+    (d / "datasets" / "toy" / "db.hex").write_text(aes_clear.ecb_encrypt(key, aes_clear.pack_u16_be(vals)).hex())
+    for exe, extra in (("client_preprocess", []), ("client_key_generation", ["4711"]), ("client_encode_encrypt", ["4712"]),
+                       ("server_preprocess_dataset", []), ("server_encrypted_aes_decryption", []),
+                       ("server_encrypted_compute", []), ("client_decrypt_decode_aes_decryption", []),
+                       ("client_postprocess_aes_decryption", []), ("client_decrypt_decode", []), ("client_postprocess", [])):
+        subprocess.run([os.path.join(BIN, exe), "0", *extra], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=900)
+    assert [int(x) for x in (d / "io" / "toy" / "result_aes.txt").read_text().split()] == vals
+    assert [int(x) for x in (d / "io" / "toy" / "result.txt").read_text().split()] == [max(vals)]
