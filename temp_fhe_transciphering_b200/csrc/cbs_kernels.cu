@@ -515,6 +515,33 @@ __device__ __forceinline__ void inv_fft_s(cplx v[8], Group &g, const Twiddles &t
     group_sync(g.bar);
     inv_p1(v, s, tw, g.t);
 }
+// shuffle-exchange variant with the rotated pass-2 twiddles in shared memory (t2xs = table[r*8 + a] + (t & 7))
+__device__ __forceinline__ void fwd_p2x_s(cplx v[8], const cplx *scr, const cplx *t2xs, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) v[mp] = scr[slot(k1, tp, mp)];
+    dft8<false>(v);
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = cmul(v[r], t2xs[r * 8]);
+}
+__device__ __forceinline__ void inv_p2x_s(cplx v[8], cplx *scr, const cplx *t2xs, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = cmul_conj(v[r], t2xs[r * 8]);
+    dft8<true>(v);
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
+}
+__device__ __forceinline__ void fill_t2x_table(cplx *t2tab, const double *twtab, int tid)
+{
+    if (tid < 64) {
+        const int a = tid >> 3, r = tid & 7;
+        const double *x = twtab + kTwiddleXOffset;
+        t2tab[r * 8 + a] = cplx{x[(512 + a * 8 + r) * 2], x[(512 + a * 8 + r) * 2 + 1]};
+    }
+}
 // fill a 64-entry shared table with the pass-2 twiddles transposed to [k2][t'] (conflict-free reads)
 __device__ __forceinline__ void fill_t2_table(cplx *t2tab, const double *twtab, int tid)
 {
@@ -527,7 +554,11 @@ __device__ __forceinline__ void fill_t2_table(cplx *t2tab, const double *twtab, 
 constexpr int kBr3GroupSmem = kGlweWords * 8 + 2 * 512 * 16;                         // 40 KB
 constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes + 64 + kBrGroups * kLweN * 2;  // + mbarriers + rotations
 
-template <bool PROF>
+// XCH = true ("v4"): the pass-2 <-> pass-3 transposes of all six transforms go through width-8 warp shuffles
+// (fft512.cuh, shuffle-exchange variant) instead of shared memory: 432 fewer shared-memory wavefronts per
+// step and ciphertext (ncu: the shared-memory data pipe, not FP64, is the busiest unit of v3) and 6 instead
+// of 12 group barriers per step.  The BSK stays in the plain transform's layout.
+template <bool PROF, bool XCH>
 __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uint64_t *__restrict__ lwe,
                                                                         uint64_t *__restrict__ acc_out, int count,
                                                                         const double *__restrict__ bsk_f,
@@ -600,7 +631,8 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
 
     // Twiddles struct view for the shared phase functions that still take t1
     Twiddles tw;
-    load_twiddles(tw, twtab, t);
+    if (XCH) load_twiddles_x(tw, twtab, t);
+    else load_twiddles(tw, twtab, t);
 
     int tile = 0;
 #pragma unroll 1
@@ -645,8 +677,13 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                 flip ^= 1;
                 fwd_p1(v, s, tw, t);
                 group_sync(bar);
-                fwd_p2(v, s, tw, t);
-                group_sync(bar);
+                if (XCH) {
+                    fwd_p2x(v, s, tw, t);
+                    exchange8<-1>(v, t & 7);
+                } else {
+                    fwd_p2(v, s, tw, t);
+                    group_sync(bar);
+                }
                 const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
                 PROF_MARK(1);  // forward passes 1-2
                 mbar_wait(full + buf, use & 1);  // requested a whole FFT ago: normally already complete
@@ -654,7 +691,8 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                 cplx kc[8], kn[8];
 #pragma unroll
                 for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];  // column 0, overlaps the last pass
-                fwd_p3(v, s, t);
+                if (XCH) fwd_p3x(v);
+                else fwd_p3(v, s, t);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     if (c < 2) {
@@ -677,9 +715,15 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
         for (int c = 0; c < 3; c++) {
             cplx *s = flip ? scr1 : scr0;
             flip ^= 1;
-            inv_p3(out[c], s, t);
-            group_sync(bar);
-            inv_p2(out[c], s, tw, t);
+            if (XCH) {
+                inv_p3x(out[c]);
+                exchange8<1>(out[c], t & 7);
+                inv_p2x(out[c], s, tw, t);
+            } else {
+                inv_p3(out[c], s, t);
+                group_sync(bar);
+                inv_p2(out[c], s, tw, t);
+            }
             group_sync(bar);
             inv_p1(out[c], s, tw, t);
             PROF_MARK(4);  // inverse transform
@@ -725,8 +769,10 @@ static int br_variant()
 {
     static int v = -1;
     if (v < 0) {
-        const char *e = getenv("CBS_BR_VARIANT");  // 0 = keys by coalesced LDG (first version, kept for A/B runs), otherwise the TMA-ring kernel (default)
-        v = e ? atoi(e) : 2;
+        // 0 = keys by coalesced LDG (first version), 2 = TMA ring + shared-memory transposes (v3),
+        // 3 = TMA ring + shuffle-exchange transforms (default); 0/2 are kept for A/B runs
+        const char *e = getenv("CBS_BR_VARIANT");
+        v = e ? atoi(e) : 3;
     }
     return v;
 }
@@ -740,8 +786,10 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     bool &attr = attr_done[attr_dev & 63];
     if (!attr) {
         cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         attr = true;
     }
     const int grid = (count + kBrGroups - 1) / kBrGroups;
@@ -758,23 +806,29 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         }
         const int full_wave = sms * kBrGroups;
         const int rem = count % full_wave;
+        const bool xch = br_variant() >= 3;
+        auto launch = [&](int blocks, int upto, int g, int base) {
+            if (xch) k_blind_rotate_v3<false, true><<<blocks, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, upto, K.bsk_f, K.tw, g, base, nullptr);
+            else k_blind_rotate_v3<false, false><<<blocks, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, upto, K.bsk_f, K.tw, g, base, nullptr);
+        };
         // last-wave balancing: a remainder that fits sms x 3 (or x 2) groups runs with fewer groups per SM
         if (split && count > full_wave && rem > 0 && rem <= sms * (kBrGroups - 1)) {
             const int head = count - rem;
             const int g = (rem + sms - 1) / sms;  // groups per CTA in the tail launch
-            k_blind_rotate_v3<false><<<head / kBrGroups, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw, kBrGroups, 0, nullptr);
-            k_blind_rotate_v3<false><<<(rem + g - 1) / g, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, g, head, nullptr);
+            launch(head / kBrGroups, head, kBrGroups, 0);
+            launch((rem + g - 1) / g, count, g, head);
         } else if (getenv("CBS_BR_PROF")) {
             static unsigned long long *d_prof = nullptr;
             if (!d_prof) cudaMalloc(&d_prof, 6 * sizeof(unsigned long long));
-            k_blind_rotate_v3<true><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, kBrGroups, 0, d_prof);
+            if (xch) k_blind_rotate_v3<true, true><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, kBrGroups, 0, d_prof);
+            else k_blind_rotate_v3<true, false><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, kBrGroups, 0, d_prof);
             unsigned long long h[6];
             cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, s);
             cudaStreamSynchronize(s);
             fprintf(stderr, "[br prof] cycles: build %llu  fwd12 %llu  tilewait %llu  p3+mac %llu  inverse %llu  torus %llu\n", h[0], h[1],
                     h[2], h[3], h[4], h[5]);
         } else {
-            k_blind_rotate_v3<false><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, kBrGroups, 0, nullptr);
+            launch(grid, count, kBrGroups, 0);
         }
     }
 }
@@ -1000,6 +1054,10 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v2(const uint64_t *
 constexpr int kTr3UnitSmem = kGlweWords * 8 + 2 * 8192 + 2 * 8192;  // cur 24 KB + 2 tiles + exchange = 56 KB
 constexpr int kTr3SmemBytes = kTr2Glwe * kTr3UnitSmem + 4 * kBrTileBytes + 1024 + 64;
 
+// XCH: shuffle-exchange transforms (fft512.cuh "x"): one shared-memory transpose and one sub-group barrier per
+// transform instead of two; both sub-groups produce spectra with the same per-lane phase, so the exchange tile and
+// the (plain-layout) key tiles are used unchanged.
+template <bool XCH>
 __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *__restrict__ in,
                                                                  uint64_t *__restrict__ out, int count, int from_acc,
                                                                  const double *__restrict__ auto_f,
@@ -1015,7 +1073,8 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + 4 * kBrTileBytes + 1024);
     uint64_t *empty = full + 4;
     const int active_units = min(kTr2Glwe, count - blockIdx.x * kTr2Glwe);
-    fill_t2_table(t2tab, twtab, threadIdx.x);
+    if (XCH) fill_t2x_table(t2tab, twtab, threadIdx.x);
+    else fill_t2_table(t2tab, twtab, threadIdx.x);
     if (threadIdx.x == 0) {
         for (int b = 0; b < 4; b++) {
             mbar_init(full + b, 1);
@@ -1051,7 +1110,8 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     const int sbar = 1 + gl * 2 + sub;
     const int ubar = 5 + gl;
     Twiddles tw;
-    load_twiddles(tw, twtab, t);
+    if (XCH) load_twiddles_x(tw, twtab, t);
+    else load_twiddles(tw, twtab, t);
     {
         const int u = threadIdx.x & 127;
         if (from_acc) {
@@ -1120,9 +1180,15 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
                 produce(want);
                 want = -1;
             }
-            fwd_p2_s(v, scr, t2s, t);
-            group_sync(sbar);
-            fwd_p3(v, scr, t);
+            if (XCH) {
+                fwd_p2x_s(v, scr, t2s, t);
+                exchange8<-1>(v, t & 7);
+                fwd_p3x(v);
+            } else {
+                fwd_p2_s(v, scr, t2s, t);
+                group_sync(sbar);
+                fwd_p3(v, scr, t);
+            }
             cplx *Xw = X + sub * 512 + t;
             const cplx *Xr = X + (1 - sub) * 512 + t;
 #pragma unroll
@@ -1156,13 +1222,23 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
         const int shift = sub ? 41 : 0;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            inv_p3(acc[c], scr, t);
-            group_sync(sbar);
-            if (producer && want >= 0) {
-                produce(want);
-                want = -1;
+            if (XCH) {
+                inv_p3x(acc[c]);
+                exchange8<1>(acc[c], t & 7);
+                if (producer && want >= 0) {
+                    produce(want);
+                    want = -1;
+                }
+                inv_p2x_s(acc[c], scr, t2s, t);
+            } else {
+                inv_p3(acc[c], scr, t);
+                group_sync(sbar);
+                if (producer && want >= 0) {
+                    produce(want);
+                    want = -1;
+                }
+                inv_p2_s(acc[c], scr, t2s, t);
             }
-            inv_p2_s(acc[c], scr, t2s, t);
             group_sync(sbar);
             inv_p1(acc[c], scr, tw, t);
             u64x2 *p = cur + c * 512;
@@ -1215,17 +1291,21 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
         }
         cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
         cudaFuncSetAttribute(k_trace_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr2SmemBytes);
-        cudaFuncSetAttribute(k_trace_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
+        cudaFuncSetAttribute(k_trace_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
+        cudaFuncSetAttribute(k_trace_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
         init = true;
     }
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("CBS_TRACE_VARIANT");
-        variant = e ? atoi(e) : 3;
+        variant = e ? atoi(e) : 4;  // 2 = LDG keys, 3 = TMA ring, 4 = TMA ring + shuffle-exchange transforms
     }
-    if (variant == 3)
-        k_trace_v3<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
-                                                                                               K.auto_f, K.tw);
+    if (variant >= 4)
+        k_trace_v3<true><<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
+                                                                                                     K.auto_f, K.tw);
+    else if (variant == 3)
+        k_trace_v3<false><<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
+                                                                                                      K.auto_f, K.tw);
     else
         k_trace_v2<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr2SmemBytes, s>>>(in, out, count, from_acc,
                                                                                                K.auto_f, K.tw);

@@ -113,8 +113,10 @@ struct Twiddles {
     cplx t2[8];  // thread u, t' = u&7:  exp(-2*pi*i*t'*k2/64),                    k2 = 0..7
 };
 
-// table layout: [64][8] t1 then [8][8] t2 (complex doubles)
-constexpr int kTwiddleTableDoubles = (64 * 8 + 8 * 8) * 2;
+// table layout: [64][8] t1 then [8][8] t2 (complex doubles), then the same two tables of the
+// shuffle-exchange variant ("x", see below): [64][8] t1x, [8][8] t2x
+constexpr int kTwiddleTableDoubles = (64 * 8 + 8 * 8) * 2 * 2;
+constexpr int kTwiddleXOffset = (64 * 8 + 8 * 8) * 2;
 
 CBS_HD void load_twiddles(Twiddles &tw, const double *table, int t)
 {
@@ -188,6 +190,64 @@ CBS_HD void inv_p1(cplx v[8], const cplx *scr, const Twiddles &tw, int t)
 #pragma unroll
     for (int m = 1; m < 8; m++) v[m] = cmul_conj(v[m], cplx{cr[m], ci[m]});
 }
+
+// ---------------------------------------------------------------------------------------------
+// Shuffle-exchange variant ("x").  ncu (profiles/r01_final_ncu_full.csv) shows the FFT kernels bound by the
+// shared-memory data pipe (64 % of peak, vs 40 % FP64): a transpose through shared memory moves every
+// value twice (STS + LDS).  The transpose between passes 2 and 3 only exchanges values among the 8 lanes
+// that share k1 = t >> 3, so it is done with 7 rounds of width-8 warp shuffles instead (each value moves
+// once, no barrier).  Round r moves register r of lane a to lane (a + r) & 7; for the register indices to
+// be compile-time constants the pass-2 outputs must sit in rotated order (register r = output (a + r) & 7)
+// and the pass-3 inputs arrive in the order tp = (b - r) & 7.  Both rotations are free:
+//   * a rotation of DFT outputs = a modulation of its inputs, folded into the pass-1 twiddle table
+//     (t1x[t][k1] = t1[t][k1] * W8^((t>>3)*(t&7))); the pass-2 twiddles are stored rotated (t2x);
+//   * a reversed+rotated input order of pass 3 = the conjugate-direction DFT-8 followed by a per-lane phase
+//     W8^(b*k3) on the spectrum.  The phase is NOT applied: the forward transform yields conj(phi) * X,
+//     the pointwise products with TRUE key spectra yield conj(phi) * OUT, and the mirrored inverse
+//     consumes exactly conj(phi) * OUT.  Key material therefore keeps the layout and values of the plain
+//     transform (keys are converted with fwd_p1..p3 above).
+// The exchange itself is a template on the lane-exchange functor so tests/cpu_emul executes the same
+// phase code with an emulated shuffle.
+CBS_HD void load_twiddles_x(Twiddles &tw, const double *table, int t) { load_twiddles(tw, table + kTwiddleXOffset, t); }
+
+// pass 2 of the forward transform: on return v[r] = Z[k1][k2 = (a + r) & 7][tp = a], a = t & 7
+CBS_HD void fwd_p2x(cplx v[8], const cplx *scr, const Twiddles &tw, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) v[mp] = scr[slot(k1, tp, mp)];
+    dft8<false>(v);
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = cmul(v[r], tw.t2[r]);
+}
+// [exchange fwd: v[r] <- lane (a - r) & 7's v[r], r = 1..7]  then pass 3:
+CBS_HD void fwd_p3x(cplx v[8]) { dft8<true>(v); }
+
+// inverse: pass 3, [exchange inv: v[r] <- lane (a + r) & 7's v[r]], pass 2 into the transpose tile
+CBS_HD void inv_p3x(cplx v[8]) { dft8<false>(v); }
+CBS_HD void inv_p2x(cplx v[8], cplx *scr, const Twiddles &tw, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = cmul_conj(v[r], tw.t2[r]);
+    dft8<true>(v);
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
+}
+
+#ifdef __CUDACC__
+// width-8 lane exchange of registers 1..7 (28 SHFL.IDX); dir = -1 forward, +1 inverse
+template <int DIR>
+__device__ __forceinline__ void exchange8(cplx v[8], int a)
+{
+#pragma unroll
+    for (int r = 1; r < 8; r++) {
+        const int src = (a + DIR * r) & 7;
+        v[r].x = __shfl_sync(0xffffffffu, v[r].x, src, 8);
+        v[r].y = __shfl_sync(0xffffffffu, v[r].y, src, 8);
+    }
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // integer <-> double helpers

@@ -47,6 +47,53 @@ static void inverse(cplx in[64][8], std::vector<double> &coef)
         }
 }
 
+// shuffle-exchange variant: same phase code, the width-8 lane exchange emulated
+static void exchange_emul(cplx v[64][8], int dir)
+{
+    cplx w[64][8];
+    memcpy(w, v, sizeof(w));
+    for (int t = 0; t < 64; t++)
+        for (int r = 1; r < 8; r++) {
+            int a = t & 7, src = (t & ~7) | ((a + dir * r) & 7);
+            v[t][r] = w[src][r];
+        }
+}
+
+static void forward_x(const std::vector<int64_t> &p, cplx out[64][8])
+{
+    static cplx scr[512];
+    cplx v[64][8];
+    Twiddles tw[64];
+    for (int t = 0; t < 64; t++) {
+        load_twiddles_x(tw[t], g_tab.data(), t);
+        for (int m = 0; m < 8; m++) v[t][m] = {(double)p[t + 64 * m], (double)p[t + 64 * m + 512]};
+    }
+    for (int t = 0; t < 64; t++) fwd_p1(v[t], scr, tw[t], t);
+    for (int t = 0; t < 64; t++) fwd_p2x(v[t], scr, tw[t], t);
+    exchange_emul(v, -1);
+    for (int t = 0; t < 64; t++) fwd_p3x(v[t]);
+    memcpy(out, v, sizeof(v));
+}
+
+static void inverse_x(cplx in[64][8], std::vector<double> &coef)
+{
+    static cplx scr[512];
+    cplx v[64][8];
+    Twiddles tw[64];
+    memcpy(v, in, sizeof(v));
+    for (int t = 0; t < 64; t++) load_twiddles_x(tw[t], g_tab.data(), t);
+    for (int t = 0; t < 64; t++) inv_p3x(v[t]);
+    exchange_emul(v, +1);
+    for (int t = 0; t < 64; t++) inv_p2x(v[t], scr, tw[t], t);
+    for (int t = 0; t < 64; t++) inv_p1(v[t], scr, tw[t], t);
+    coef.assign(1024, 0.0);
+    for (int t = 0; t < 64; t++)
+        for (int m = 0; m < 8; m++) {
+            coef[t + 64 * m] = v[t][m].x;
+            coef[t + 64 * m + 512] = v[t][m].y;
+        }
+}
+
 static int check_banks()
 {
     // a quarter-warp (8 consecutive lanes) must touch 8 distinct 16-byte slots modulo 8
@@ -112,6 +159,21 @@ int main()
             }
             e3 = fmax(e3, fmax(fabs((double)sr - fa[u][k3].x), fabs((double)si - fa[u][k3].y)));
         }
+    // (3) shuffle-exchange variant: round trip, and data through forward_x/inverse_x multiplied by a key
+    //     spectrum from the PLAIN forward transform must still give the negacyclic convolution
+    double e4 = 0, e5 = 0;
+    {
+        cplx xa[64][8], xc[64][8];
+        forward_x(a, xa);
+        std::vector<double> bx;
+        inverse_x(xa, bx);
+        for (int i = 0; i < 1024; i++) e4 = fmax(e4, fabs(bx[i] / 512.0 - (double)a[i]));
+        for (int t = 0; t < 64; t++)
+            for (int k = 0; k < 8; k++) xc[t][k] = cmul(xa[t][k], fb[t][k]);
+        std::vector<double> cx;
+        inverse_x(xc, cx);
+        for (int i = 0; i < 1024; i++) e5 = fmax(e5, fabs(cx[i] / 512.0 - ref[i]));
+    }
     int bad = check_banks();
     // (4) helpers
     int bad_dec = 0;
@@ -143,7 +205,7 @@ int main()
         uint64_t w = (want >= 9223372036854775808.0L) ? 0x8000000000000000ull : (uint64_t)(int64_t)want;
         if (got != w) bad_tor++;
     }
-    printf("roundtrip_err=%.3e conv_err=%.3e bin_err=%.3e bank_conflicts=%d bad_decomp=%d bad_torus=%d\n", e1, e2, e3, bad,
-           bad_dec, bad_tor);
-    return (e1 < 1e-9 && e2 < 1e-3 && e3 < 1e-6 && bad == 0 && bad_dec == 0 && bad_tor == 0) ? 0 : 1;
+    printf("roundtrip_err=%.3e conv_err=%.3e bin_err=%.3e x_roundtrip_err=%.3e x_conv_err=%.3e bank_conflicts=%d bad_decomp=%d bad_torus=%d\n",
+           e1, e2, e3, e4, e5, bad, bad_dec, bad_tor);
+    return (e1 < 1e-9 && e2 < 1e-3 && e3 < 1e-6 && e4 < 1e-9 && e5 < 1e-3 && bad == 0 && bad_dec == 0 && bad_tor == 0) ? 0 : 1;
 }
