@@ -177,6 +177,17 @@ int cbs_aes128_ctr_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, con
  * (sequential fold); any nvals >= 1 is reduced as a balanced tree here. */
 int cbs_max_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out);
 
+/* Mini-workload #2 of the harness (harness/cleartext_impl.py:65-70, README.md:43; the reference submission has
+ * no implementation): encrypted  sum_i (x_i * y_i mod 2^16) mod 2^16  with x = the first nvals/2 values and
+ * y = the second half; in[nvals][16] big LWE (MSB first, the payload of ciphertext_aes_download/result.bin)
+ * -> out[16] big LWE (MSB first).  nvals must be even.  Boolean circuit of nibble-product, population-count
+ * and nibble-adder LUT ladders over circuit-bootstrapped bits (csrc/host/ip_plan.h). */
+int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out);
+/* Host-only dry run of the SAME circuit plan on cleartext values (no GPU, no ciphertexts): checks the circuit
+ * against the harness formula in the CPU test suite and reports its size.  Any output pointer may be NULL. */
+int cbs_inner_product_plan_check(const uint16_t *vals, int nvals, uint16_t *result, int64_t *circuit_bootstraps,
+                                 int *layers, int64_t *lut_ladders);
+
 /* ---------------------------------------------------------------------------------------------
  * Device-resident variants (inputs/outputs already in HBM, asynchronous on the context's stream).
  * Used by bench.py's `value` leg and by callers that keep state on the GPU. */

@@ -65,6 +65,20 @@ def lib():
     return _lib
 
 
+def inner_product_plan_check(vals):
+    """Host-only dry run of the inner-product circuit on cleartext u16 values -> (result, circuit bootstraps,
+    layers, LUT ladders).  Checks the circuit plan, never touches the GPU."""
+    v = np.ascontiguousarray(vals, dtype=np.uint16)
+    res = ctypes.c_uint16()
+    ncbs = ctypes.c_int64()
+    layers = ctypes.c_int()
+    ladders = ctypes.c_int64()
+    _check(lib().cbs_inner_product_plan_check(v.ctypes.data_as(ctypes.c_void_p), int(v.size), ctypes.byref(res),
+                                              ctypes.byref(ncbs), ctypes.byref(layers), ctypes.byref(ladders)),
+           "cbs_inner_product_plan_check")
+    return int(res.value), int(ncbs.value), int(layers.value), int(ladders.value)
+
+
 def _check(rc, what):
     if rc != 0:
         raise CbsError(f"{what} failed (code {rc}): {lib().cbs_last_error().decode()}")
@@ -377,6 +391,15 @@ class Context:
         nvals = a.shape[0] // 16
         out, po = _out((16, LWE_BIG))
         _check(lib().cbs_max_u16(self._h, pi, nvals, po), "cbs_max_u16")
+        return out
+
+    def inner_product_u16(self, lwe_bits):
+        """mini-workload #2 (harness/cleartext_impl.py:65-70): [nvals*16][2049] -> [16][2049] encrypting
+        sum_i (x_i * y_i mod 2^16) mod 2^16, x = first half of the values, y = second half."""
+        a, pi = _u64(np.reshape(lwe_bits, (-1, LWE_BIG)))
+        nvals = a.shape[0] // 16
+        out, po = _out((16, LWE_BIG))
+        _check(lib().cbs_inner_product_u16(self._h, pi, nvals, po), "cbs_inner_product_u16")
         return out
 
     def measure_fp64_tflops(self):

@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include "host/ip_plan.h"
+
 using namespace cbs;
 using cbs_host::set_error;
 
@@ -976,6 +978,109 @@ int cbs_max_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
         cur ^= 1;
     }
     return download(ctx, out, d_lwe[cur], vals_lwe * 8);
+}
+
+// Mini-workload #2 of the harness (harness/cleartext_impl.py:65-70; no reference implementation exists, SURVEY.md
+// 8(f)2): sum_i (x_i * y_i mod 2^16) mod 2^16 with x = first half, y = second half of the values.  The circuit
+// (nibble products, column compression by population counts, nibble adders) is planned on the host by
+// host/ip_plan.h; every layer is [gather -> LWE keyswitch -> circuit bootstrap -> gathered LUT ladders].
+int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
+{
+    ENTER(ctx);
+    if (nvals <= 0 || (nvals & 1) || !in || !out) return set_error("cbs_inner_product_u16: bad argument (need an even number of values)"), CBS_ERR_ARG;
+    using namespace cbs_host;
+    const IpPlan plan = ip_make_plan(nvals);
+    constexpr int kCap = 8192;  // circuit bootstraps per sub-batch (bounds the Fourier GGSW workspace to 4.2 GB)
+
+    // flatten the plan into sub-batches of jobs whose selectors fit the cap
+    struct Batch {
+        int idx_off, m, job_off, njobs;
+    };
+    std::vector<Batch> batches;
+    std::vector<int> h_idx, h_sel, h_lut, h_out;
+    for (const IpLayer &L : plan.layers) {
+        std::vector<int> remap(L.cbs.size(), -1);
+        std::vector<int> touched;
+        Batch b{(int)h_idx.size(), 0, (int)h_lut.size(), 0};
+        auto flush = [&]() {
+            if (b.njobs) batches.push_back(b);
+            for (int pos : touched) remap[(size_t)pos] = -1;
+            touched.clear();
+            b = Batch{(int)h_idx.size(), 0, (int)h_lut.size(), 0};
+        };
+        for (const IpJob &j : L.jobs) {
+            int fresh = 0;
+            for (int i = 0; i < 8; i++)
+                if (j.sel[i] >= 0 && remap[(size_t)j.sel[i]] < 0) fresh++;
+            if (b.m + fresh > kCap) flush();
+            for (int i = 0; i < 8; i++) {
+                int v = -1;
+                if (j.sel[i] >= 0) {
+                    int &r = remap[(size_t)j.sel[i]];
+                    if (r < 0) {
+                        r = b.m++;
+                        touched.push_back(j.sel[i]);
+                        h_idx.push_back(L.cbs[(size_t)j.sel[i]]);
+                    }
+                    v = r;
+                }
+                h_sel.push_back(v);
+            }
+            h_lut.push_back(j.lut * 2 + j.acc);
+            h_out.push_back(j.out);
+            b.njobs++;
+        }
+        flush();
+    }
+    int max_m = 1;
+    for (const Batch &b : batches) max_m = b.m > max_m ? b.m : max_m;
+    for (int i = 0; i < 16; i++) h_idx.push_back(plan.result[15 - i]);  // final gather, MSB first
+
+    // trivial LUT accumulators: coefficient i carries bit (4*acc + i/256) of table[i % 256] at 2^63
+    // (same layout as generate_vec_keyed_lut_accumulator, cbs_lib/src/aes_he.rs:835-875)
+    std::vector<uint64_t> h_luts((size_t)kIpNumLuts * 2 * kGlweWords, 0);
+    for (int l = 0; l < kIpNumLuts; l++)
+        for (int a = 0; a < 2; a++) {
+            uint64_t *body = h_luts.data() + (size_t)(l * 2 + a) * kGlweWords + 2048;
+            for (int i = 0; i < 1024; i++) body[i] = (uint64_t)((ip_lut_value(l, (unsigned)(i % 256)) >> (4 * a + i / 256)) & 1u) << 63;
+        }
+
+    uint64_t *d_pool, *d_rows, *d_ks, *d_luts;
+    double *d_ggsw_f;
+    int *d_idx, *d_sel, *d_lut, *d_out;
+    TRY(ws_typed(ctx, "ip_pool", (size_t)plan.pool_size * kLweBig, &d_pool));
+    TRY(ws_typed(ctx, "ip_rows", (size_t)max_m * kLweBig, &d_rows));
+    TRY(ws_typed(ctx, "ks", (size_t)max_m * kLweSmall, &d_ks));
+    TRY(ws_typed(ctx, "ggsw_f", (size_t)max_m * kGgswWords, &d_ggsw_f));
+    TRY(ws_typed(ctx, "ip_luts", h_luts.size(), &d_luts));
+    TRY(ws_typed(ctx, "ip_idx", h_idx.size(), &d_idx));
+    TRY(ws_typed(ctx, "ip_sel", h_sel.size() + 1, &d_sel));
+    TRY(ws_typed(ctx, "ip_lut", h_lut.size() + 1, &d_lut));
+    TRY(ws_typed(ctx, "ip_out", h_out.size() + 1, &d_out));
+    TRY(upload(ctx, d_pool, in, (size_t)nvals * 16 * kLweBig * 8));
+    TRY(upload(ctx, d_luts, h_luts.data(), h_luts.size() * 8));
+    TRY(upload(ctx, d_idx, h_idx.data(), h_idx.size() * sizeof(int)));
+    if (!h_lut.empty()) {
+        TRY(upload(ctx, d_sel, h_sel.data(), h_sel.size() * sizeof(int)));
+        TRY(upload(ctx, d_lut, h_lut.data(), h_lut.size() * sizeof(int)));
+        TRY(upload(ctx, d_out, h_out.data(), h_out.size() * sizeof(int)));
+    }
+    for (const Batch &b : batches) {
+        launch_gather_lwe(d_pool, d_idx + b.idx_off, d_rows, b.m, ctx->stream);
+        ctx->launches++;
+        TRY(check_launch("k_gather_lwe"));
+        TRY(dev_keyswitch(ctx, d_rows, d_ks, b.m));
+        TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, b.m));
+        launch_lut8_gather(ctx->K, d_ggsw_f, d_sel + (size_t)b.job_off * 8, d_luts, d_lut + b.job_off, d_out + b.job_off, d_pool,
+                           b.njobs, ctx->stream);
+        ctx->launches++;
+        TRY(check_launch("k_lut8_gather"));
+    }
+    launch_gather_lwe(d_pool, d_idx + (h_idx.size() - 16), d_rows, 16, ctx->stream);
+    ctx->launches++;
+    TRY(check_launch("k_gather_lwe"));
+    // download() synchronises the stream, so the host tables above outlive every asynchronous copy
+    return download(ctx, out, d_rows, (size_t)16 * kLweBig * 8);
 }
 
 }  // extern "C"

@@ -515,33 +515,6 @@ __device__ __forceinline__ void inv_fft_s(cplx v[8], Group &g, const Twiddles &t
     group_sync(g.bar);
     inv_p1(v, s, tw, g.t);
 }
-// shuffle-exchange variant with the rotated pass-2 twiddles in shared memory (t2xs = table[r*8 + a] + (t & 7))
-__device__ __forceinline__ void fwd_p2x_s(cplx v[8], const cplx *scr, const cplx *t2xs, int t)
-{
-    const int k1 = t >> 3, tp = t & 7;
-#pragma unroll
-    for (int mp = 0; mp < 8; mp++) v[mp] = scr[slot(k1, tp, mp)];
-    dft8<false>(v);
-#pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = cmul(v[r], t2xs[r * 8]);
-}
-__device__ __forceinline__ void inv_p2x_s(cplx v[8], cplx *scr, const cplx *t2xs, int t)
-{
-    const int k1 = t >> 3, tp = t & 7;
-#pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = cmul_conj(v[r], t2xs[r * 8]);
-    dft8<true>(v);
-#pragma unroll
-    for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
-}
-__device__ __forceinline__ void fill_t2x_table(cplx *t2tab, const double *twtab, int tid)
-{
-    if (tid < 64) {
-        const int a = tid >> 3, r = tid & 7;
-        const double *x = twtab + kTwiddleXOffset;
-        t2tab[r * 8 + a] = cplx{x[(512 + a * 8 + r) * 2], x[(512 + a * 8 + r) * 2 + 1]};
-    }
-}
 // fill a 64-entry shared table with the pass-2 twiddles transposed to [k2][t'] (conflict-free reads)
 __device__ __forceinline__ void fill_t2_table(cplx *t2tab, const double *twtab, int tid)
 {
@@ -1054,10 +1027,8 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v2(const uint64_t *
 constexpr int kTr3UnitSmem = kGlweWords * 8 + 2 * 8192 + 2 * 8192;  // cur 24 KB + 2 tiles + exchange = 56 KB
 constexpr int kTr3SmemBytes = kTr2Glwe * kTr3UnitSmem + 4 * kBrTileBytes + 1024 + 64;
 
-// XCH: shuffle-exchange transforms (fft512.cuh "x"): one shared-memory transpose and one sub-group barrier per
-// transform instead of two; both sub-groups produce spectra with the same per-lane phase, so the exchange tile and
-// the (plain-layout) key tiles are used unchanged.
-template <bool XCH>
+// (Tried and rejected: the shuffle-exchange transforms of the blind rotation in this kernel - 5.3 ms instead of
+//  3.8 ms per 7168 GLWE at 255 registers with spills, so the trace keeps the shared-memory transposes.)
 __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *__restrict__ in,
                                                                  uint64_t *__restrict__ out, int count, int from_acc,
                                                                  const double *__restrict__ auto_f,
@@ -1073,8 +1044,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + 4 * kBrTileBytes + 1024);
     uint64_t *empty = full + 4;
     const int active_units = min(kTr2Glwe, count - blockIdx.x * kTr2Glwe);
-    if (XCH) fill_t2x_table(t2tab, twtab, threadIdx.x);
-    else fill_t2_table(t2tab, twtab, threadIdx.x);
+    fill_t2_table(t2tab, twtab, threadIdx.x);
     if (threadIdx.x == 0) {
         for (int b = 0; b < 4; b++) {
             mbar_init(full + b, 1);
@@ -1110,8 +1080,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     const int sbar = 1 + gl * 2 + sub;
     const int ubar = 5 + gl;
     Twiddles tw;
-    if (XCH) load_twiddles_x(tw, twtab, t);
-    else load_twiddles(tw, twtab, t);
+    load_twiddles(tw, twtab, t);
     {
         const int u = threadIdx.x & 127;
         if (from_acc) {
@@ -1180,15 +1149,9 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
                 produce(want);
                 want = -1;
             }
-            if (XCH) {
-                fwd_p2x_s(v, scr, t2s, t);
-                exchange8<-1>(v, t & 7);
-                fwd_p3x(v);
-            } else {
-                fwd_p2_s(v, scr, t2s, t);
-                group_sync(sbar);
-                fwd_p3(v, scr, t);
-            }
+            fwd_p2_s(v, scr, t2s, t);
+            group_sync(sbar);
+            fwd_p3(v, scr, t);
             cplx *Xw = X + sub * 512 + t;
             const cplx *Xr = X + (1 - sub) * 512 + t;
 #pragma unroll
@@ -1222,23 +1185,13 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
         const int shift = sub ? 41 : 0;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            if (XCH) {
-                inv_p3x(acc[c]);
-                exchange8<1>(acc[c], t & 7);
-                if (producer && want >= 0) {
-                    produce(want);
-                    want = -1;
-                }
-                inv_p2x_s(acc[c], scr, t2s, t);
-            } else {
-                inv_p3(acc[c], scr, t);
-                group_sync(sbar);
-                if (producer && want >= 0) {
-                    produce(want);
-                    want = -1;
-                }
-                inv_p2_s(acc[c], scr, t2s, t);
+            inv_p3(acc[c], scr, t);
+            group_sync(sbar);
+            if (producer && want >= 0) {
+                produce(want);
+                want = -1;
             }
+            inv_p2_s(acc[c], scr, t2s, t);
             group_sync(sbar);
             inv_p1(acc[c], scr, tw, t);
             u64x2 *p = cur + c * 512;
@@ -1291,21 +1244,17 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
         }
         cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
         cudaFuncSetAttribute(k_trace_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr2SmemBytes);
-        cudaFuncSetAttribute(k_trace_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
-        cudaFuncSetAttribute(k_trace_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
+        cudaFuncSetAttribute(k_trace_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
         init = true;
     }
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("CBS_TRACE_VARIANT");
-        variant = e ? atoi(e) : 4;  // 2 = LDG keys, 3 = TMA ring, 4 = TMA ring + shuffle-exchange transforms
+        variant = e ? atoi(e) : 3;
     }
-    if (variant >= 4)
-        k_trace_v3<true><<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
-                                                                                                     K.auto_f, K.tw);
-    else if (variant == 3)
-        k_trace_v3<false><<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
-                                                                                                      K.auto_f, K.tw);
+    if (variant == 3)
+        k_trace_v3<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
+                                                                                               K.auto_f, K.tw);
     else
         k_trace_v2<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr2SmemBytes, s>>>(in, out, count, from_acc,
                                                                                                K.auto_f, K.tw);
@@ -1670,6 +1619,103 @@ __global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8(const double *__res
         }
         if (t == 0) o[2048] = acc[2048 + T];
     }
+}
+
+// ---- LUT ladder with gathered selectors (inner-product circuit, host/ip_plan.h) ---------------------------
+// Same ladder as k_lut8, but the 8 selector GGSWs of a job are picked by index (sel[job][i], -1 = the
+// selector is the constant 0: the CMux is the identity and is skipped), so one circuit-bootstrapped bit can
+// feed several ladders and ladders may have fewer than 8 inputs.
+__global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8_gather(const double *__restrict__ ggsw_f,
+                                                                     const int *__restrict__ sel,
+                                                                     const uint64_t *__restrict__ luts,
+                                                                     const int *__restrict__ lut_index,
+                                                                     const int *__restrict__ out_index,
+                                                                     uint64_t *__restrict__ out, int njobs,
+                                                                     const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6;
+    const int job = blockIdx.x * kLutGroups + gi;
+    if (job >= njobs) return;
+    unsigned char *base = smem_raw + (size_t)gi * kLutGroupSmem;
+    uint64_t *acc = reinterpret_cast<uint64_t *>(base);
+    Group g;
+    g.t = threadIdx.x & 63;
+    g.bar = 1 + gi;
+    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+    g.scr1 = g.scr0 + 512;
+    g.flip = 0;
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
+    const int t = g.t;
+    const uint64_t *src = luts + (size_t)lut_index[job] * kGlweWords;
+    for (int w = t; w < kGlweWords; w += 64) acc[w] = src[w];
+    group_sync(g.bar);
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        const int which = sel[job * 8 + i];
+        if (which < 0) continue;
+        const int d = 1 << i;
+        cplx o[3][8];
+        cbs_external_product(o, ggsw_f + (size_t)which * kGgswWords, g, tw, [&](int r, int j) {
+            return neg_read(acc + r * 1024, (j + d) & 2047) - acc[r * 1024 + j];  // acc * X^-d - acc
+        });
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            inv_fft(o[c], g, tw);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                acc[c * 1024 + t + 64 * m] += torus_from_scaled(o[c][m].x);
+                acc[c * 1024 + t + 64 * m + 512] += torus_from_scaled(o[c][m].y);
+            }
+        }
+    }
+    group_sync(g.bar);
+    for (int q = 0; q < 4; q++) {
+        const int T = 256 * q;
+        uint64_t *o = out + (size_t)(out_index[job] + q) * kLweBig;
+        for (int w = t; w < 2048; w += 64) {
+            const int c = w >> 10, j = w & 1023;
+            const uint64_t *mp = acc + c * 1024;
+            o[w] = (j <= T) ? mp[T - j] : (0ull - mp[1024 + T - j]);
+        }
+        if (t == 0) o[2048] = acc[2048 + T];
+    }
+}
+
+void launch_lut8_gather(const DeviceKeys &K, const double *ggsw_f, const int *sel, const uint64_t *luts, const int *lut_index,
+                        const int *out_index, uint64_t *out, int njobs, cudaStream_t s)
+{
+    if (njobs <= 0) return;
+    static bool attr_done[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    if (!attr_done[attr_dev & 63]) {
+        cudaFuncSetAttribute(k_lut8_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutSmemBytes);
+        attr_done[attr_dev & 63] = true;
+    }
+    k_lut8_gather<<<(njobs + kLutGroups - 1) / kLutGroups, 64 * kLutGroups, kLutSmemBytes, s>>>(ggsw_f, sel, luts, lut_index,
+                                                                                                 out_index, out, njobs, K.tw);
+}
+
+// rows[i] = pool[idx[i]] (LWE(2048) ciphertexts); idx < 0 gives the trivial encryption of 0
+__global__ void k_gather_lwe(const uint64_t *__restrict__ pool, const int *__restrict__ idx, uint64_t *__restrict__ rows)
+{
+    const int i = blockIdx.x;
+    const int src = idx[i];
+    uint64_t *o = rows + (size_t)i * kLweBig;
+    if (src < 0) {
+        for (int w = threadIdx.x; w < kLweBig; w += blockDim.x) o[w] = 0;
+    } else {
+        const uint64_t *p = pool + (size_t)src * kLweBig;
+        for (int w = threadIdx.x; w < kLweBig; w += blockDim.x) o[w] = p[w];
+    }
+}
+
+void launch_gather_lwe(const uint64_t *pool, const int *idx, uint64_t *rows, int count, cudaStream_t s)
+{
+    if (count <= 0) return;
+    k_gather_lwe<<<count, 256, 0, s>>>(pool, idx, rows);
 }
 
 // ---- LUT ladder v2: GGSW row tiles staged through the same 2-deep TMA ring as the blind rotation --------

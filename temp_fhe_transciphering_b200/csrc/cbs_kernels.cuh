@@ -65,6 +65,13 @@ void launch_ggsw_to_fourier(const DeviceKeys &K, const uint64_t *ggsw_std, doubl
 void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts, const int *lut_index,
                  const int *out_index, uint64_t *out, int njobs, int accs_per_byte, int trivial, cudaStream_t s);
 
+// a7 with gathered selectors (inner-product circuit): job j runs the ladder over the GGSWs ggsw_f[sel[j*8 + i]]
+//     (i = 0..7, -1 = constant-0 selector) on accumulator luts[lut_index[j]], 4 LWE(2048) out at out[out_index[j] + q]
+void launch_lut8_gather(const DeviceKeys &K, const double *ggsw_f, const int *sel, const uint64_t *luts, const int *lut_index,
+                        const int *out_index, uint64_t *out, int njobs, cudaStream_t s);
+// rows[i] = pool[idx[i]] for LWE(2048) ciphertexts (idx < 0: trivial zero)
+void launch_gather_lwe(const uint64_t *pool, const int *idx, uint64_t *rows, int count, cudaStream_t s);
+
 // a8  rounds 10+9: sample extraction from the encrypted keyed LUTs (ct = raw AES ciphertext bytes; the cleartext inv_shift_rows is applied inside)
 //     luts = [nmult][16][2] GLWE, tm = [nmult][nblocks][128][2049]; inv_shift = 1 for the inverse direction
 void launch_known_rotate(const uint8_t *ct, const uint64_t *luts, uint64_t *tm, int nblocks, int nmult, int inv_shift,

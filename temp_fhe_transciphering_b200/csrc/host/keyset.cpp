@@ -9,6 +9,7 @@
 // src/data_struct.rs:30-269 + src/aes_manager.rs:163-432 (AllRdKeys tables).
 #include "cbs_b200.h"
 #include "host_common.h"
+#include "ip_plan.h"
 
 #include <algorithm>
 #include <array>
@@ -1044,6 +1045,26 @@ int cbs_u64_vec_load(const char *path, uint64_t **data, uint64_t *n)
     memcpy(p, r.buf.data() + r.off, 8 * len);
     *data = p;
     *n = len;
+    return CBS_OK;
+}
+
+// dry run of the inner-product circuit plan on cleartext values (test hook of host/ip_plan.h)
+int cbs_inner_product_plan_check(const uint16_t *vals, int nvals, uint16_t *result, int64_t *circuit_bootstraps, int *layers,
+                                 int64_t *lut_ladders)
+{
+    if (nvals <= 0 || (nvals & 1) || (!vals && result)) {
+        set_error("cbs_inner_product_plan_check: bad argument (need an even number of values)");
+        return CBS_ERR_ARG;
+    }
+    const IpPlan plan = ip_make_plan(nvals);
+    if (result) *result = ip_eval_clear(plan, vals);
+    if (circuit_bootstraps) *circuit_bootstraps = plan.total_cbs();
+    if (layers) *layers = (int)plan.layers.size();
+    if (lut_ladders) {
+        int64_t n = 0;
+        for (const IpLayer &l : plan.layers) n += (int64_t)l.jobs.size();
+        *lut_ladders = n;
+    }
     return CBS_OK;
 }
 

@@ -212,3 +212,19 @@ def test_max_u16(ctx, keyset):
     dec, std, mx = ref_io.noise_stats(got, keyset.glwe_sk)
     assert ref_io.bits_to_u16(dec) == [max(vals)]
     assert mx < 61.5
+
+
+def test_inner_product_u16(ctx, keyset):
+    """mini-workload #2: decrypted result bit-exact against harness/cleartext_impl.py:65-70 (toy = 8 values)."""
+    import ref_io
+    for seed, n in ((1, 8), (2, 2), (3, 20)):
+        vals = np.random.default_rng(seed).integers(0, 65536, n).tolist()
+        if seed == 2:
+            vals = [65535, 65535]
+        bits = np.array([(v >> (15 - i)) & 1 for v in vals for i in range(16)], dtype=np.uint8)
+        lwe = keyset.encrypt_bits_big(bits, 40 + seed)
+        got = ctx.inner_product_u16(lwe)
+        dec, std, mx = ref_io.noise_stats(got, keyset.glwe_sk)
+        want = sum((x * y) % 65536 for x, y in zip(vals[: n // 2], vals[n // 2:])) % 65536
+        assert ref_io.bits_to_u16(dec) == [want], (n, vals)
+        assert mx < 61.5

@@ -278,3 +278,28 @@ def test_client_stage_tools_match_reference_clients(cbs, keyset, tmp_path):
     assert outs["ours"]["result.txt"].decode().split() == [str(vals[0])]
     if "ref" in outs:
         assert outs["ours"] == outs["ref"]
+
+
+def test_inner_product_circuit_plan_matches_harness_formula(cbs):
+    """The Boolean circuit the GPU executes for mini-workload #2 (csrc/host/ip_plan.h), dry-run on cleartext
+    bits, against harness/cleartext_impl.py:65-70; sizes = toy / small / medium value counts and edge cases."""
+    def formula(v):
+        h = len(v) // 2
+        return sum((int(x) * int(y)) % 65536 for x, y in zip(v[:h], v[h:])) % 65536
+
+    rng = np.random.default_rng(5)
+    for n in (2, 4, 8, 10, 64, 512):
+        for trial in range(20):
+            v = rng.integers(0, 65536, n, dtype=np.uint16)
+            if trial == 0:
+                v[:] = 65535
+            if trial == 1:
+                v[:] = 0
+            if trial == 2:
+                v[: n // 2] = 1
+            got, ncbs, layers, ladders = cbs.inner_product_plan_check(v)
+            assert got == formula(v), (n, trial)
+    # circuit size of the three harness instances (workload_specification.md:8-9: 8 / 64 / 512 values)
+    assert [cbs.inner_product_plan_check(np.zeros(n, np.uint16))[1:3] for n in (8, 64, 512)] == [(600, 9), (4402, 11), (34654, 13)]
+    with pytest.raises(cbs.CbsError):
+        cbs.inner_product_plan_check(np.zeros(3, np.uint16))

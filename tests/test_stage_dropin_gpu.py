@@ -100,3 +100,9 @@ def test_all_ten_stages_ours(tmp_path):
         subprocess.run([os.path.join(BIN, exe), "0", *extra], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=900)
     assert [int(x) for x in (d / "io" / "toy" / "result_aes.txt").read_text().split()] == vals
     assert [int(x) for x in (d / "io" / "toy" / "result.txt").read_text().split()] == [max(vals)]
+    # mini-workload #2 (harness --mini_workload 1): inner product of the two halves mod 2^16
+    env = dict(os.environ, CBS_MINI_WORKLOAD="1")
+    for exe in ("server_encrypted_compute", "client_decrypt_decode", "client_postprocess"):
+        subprocess.run([os.path.join(BIN, exe), "0"], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=900, env=env)
+    want = sum((x * y) % 65536 for x, y in zip(vals[:4], vals[4:])) % 65536
+    assert [int(x) for x in (d / "io" / "toy" / "result.txt").read_text().split()] == [want]
