@@ -338,6 +338,7 @@ def main_ours(args):
     # --- mini-workload of the small instance: encrypted max over the 8*nblocks transciphered u16 values
     #     (stage 8, server_encrypted_compute.rs), host buffers through the C ABI; reported, not part of `value` ---
     maxw = None
+    ipw = None
     if rank == 0:
         res = h_out_t.numpy().view(np.uint64).reshape(-1, 2049)
         torch.cuda.synchronize()
@@ -347,6 +348,17 @@ def main_ours(args):
         got = ref_io.bits_to_u16(ref_io.decode_bit(ref_io.lwe_phase(mx_ct, ks.glwe_sk)))[0]
         want = max(aes_clear.unpack_u16_be(pt))
         maxw = {"values": 8 * nblocks, "seconds": t_max, "verified": bool(got == want)}
+        # mini-workload #2 (harness/cleartext_impl.py:65-70): inner product mod 2^16 of the two halves
+        vals = aes_clear.unpack_u16_be(pt)
+        t0 = time.perf_counter()
+        ip_ct = ctx.inner_product_u16(res)
+        t_ip = time.perf_counter() - t0
+        got = ref_io.bits_to_u16(ref_io.decode_bit(ref_io.lwe_phase(ip_ct, ks.glwe_sk)))[0]
+        h = len(vals) // 2
+        want = sum((x * y) % 65536 for x, y in zip(vals[:h], vals[h:])) % 65536
+        _, n_cbs, n_layers, n_ladders = cbs.inner_product_plan_check(np.array(vals, dtype=np.uint16))
+        ipw = {"values": 8 * nblocks, "seconds": t_ip, "verified": bool(got == want), "circuit_bootstraps": n_cbs,
+               "layers": n_layers, "lut_ladders": n_ladders}
 
     # --- roofline of the dominant kernel (blind rotation), timed alone with CUDA events ---
     roof = None
@@ -410,6 +422,7 @@ def main_ours(args):
             "verified": bool(verified), "output_noise_log2_std": std, "output_noise_log2_max": mx,
             "roofline": roof,
             "max_u16_miniworkload": maxw,
+            "inner_product_u16_miniworkload": ipw,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

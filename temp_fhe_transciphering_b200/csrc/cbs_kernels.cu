@@ -469,6 +469,32 @@ __device__ __forceinline__ int32_t digit_b23_l1(uint64_t x)
     return (int32_t)s - ((s > (1u << 22)) ? (1 << 23) : 0);
 }
 
+// The same digit from the high word of x only, directly as a double.  With hi = x >> 32:
+//   s = ((hi >> 8) + 1) >> 1,  digit = s - (s > 2^22 ? 2^23 : 0)   ==   (((int32)(hi - 0x100)) >> 9) + 1
+// (digit_b23_l1_hi in fft512.cuh, checked against the generic decomposer in tests/cpu_emul); digit + 2^31 is the low word of the magic
+// number 2^52 + 2^31 + digit, so the conversion is three integer instructions and one DADD.
+__device__ __forceinline__ double digit_b23_l1_double(uint32_t hi)
+{
+    const uint32_t lo = (uint32_t)(((int32_t)(hi - 0x100u)) >> 9) + 0x80000001u;
+    return __hiloint2double(0x43300000, (int)lo) - 4503601774854144.0;
+}
+// high word of ((X ^ M) - M) - O for the 64-bit X = (xh:xl), O = (oh:ol) and M = (m:m), m = 0 or ~0:
+// the conditional negation of X folded into the subtraction of the own coefficient
+__device__ __forceinline__ uint32_t hi_condneg_sub(uint32_t xl, uint32_t xh, uint32_t m, uint32_t ol, uint32_t oh)
+{
+    uint32_t hi;
+    asm("{\n\t.reg .u32 a, b;\n\t"
+        "xor.b32 a, %1, %3;\n\t"
+        "xor.b32 b, %2, %3;\n\t"
+        "sub.cc.u32 a, a, %3;\n\t"
+        "subc.u32 b, b, %3;\n\t"
+        "sub.cc.u32 a, a, %4;\n\t"
+        "subc.u32 %0, b, %5;\n\t}"
+        : "=r"(hi)
+        : "r"(xl), "r"(xh), "r"(m), "r"(ol), "r"(oh));
+    return hi;
+}
+
 struct __align__(16) u64x2 {
     uint64_t lo, hi;
 };
@@ -531,6 +557,8 @@ constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes
 // (fft512.cuh, shuffle-exchange variant) instead of shared memory: 432 fewer shared-memory wavefronts per
 // step and ciphertext (ncu: the shared-memory data pipe, not FP64, is the busiest unit of v3) and 6 instead
 // of 12 group barriers per step.  The BSK stays in the plain transform's layout.
+// (Tried and rejected: a producer lane that polls the ring's `empty` barriers with mbarrier.test_wait at four points of
+//  every polynomial instead of blocking at the top of it: 6.04 vs 5.83 ms per wave.)
 template <bool PROF, bool XCH>
 __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uint64_t *__restrict__ lwe,
                                                                         uint64_t *__restrict__ acc_out, int count,
@@ -570,6 +598,7 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
     constexpr int kTiles = kLweN * 3;
     if (producer)
         for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
+    __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
 
     unsigned char *base = smem_raw + (size_t)gi * kBr3GroupSmem;
     u64x2 *acc = reinterpret_cast<u64x2 *>(base);  // [3][512] pairs (coef j, coef j + 512)
@@ -628,6 +657,7 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                 tma_load_tile(ring + pb * kBrTileBytes, bsk_bytes + (size_t)(tile - 1 + kBrRing) * kBrTileBytes, kBrTileBytes,
                               full + pb);
             }
+            __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
             if (!skip) {
                 cplx v[8];
                 const u64x2 *p = acc + r * 512;
@@ -635,15 +665,20 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                 for (int m = 0; m < 8; m++) {
                     const int jj = t + 64 * m;
                     const int e0 = (jj - d) & 2047;
-                    const u64x2 src = p[e0 & 511];
-                    const u64x2 own = p[jj];
-                    const int h = e0 >> 9;  // quarter of the 2N-periodic extension
-                    // (rot_lo, rot_hi) = h0:(lo,hi) h1:(hi,-lo) h2:(-lo,-hi) h3:(-hi,lo)
-                    uint64_t rl = (h & 1) ? src.hi : src.lo;
-                    uint64_t rh = (h & 1) ? src.lo : src.hi;
-                    if (h >= 2) rl = 0ull - rl;
-                    if (h == 1 || h == 2) rh = 0ull - rh;
-                    v[m] = cplx{i32_to_double(digit_b23_l1(rl - own.lo)), i32_to_double(digit_b23_l1(rh - own.hi))};
+                    const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];  // (lo.l, lo.h, hi.l, hi.h)
+                    const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
+                    // quarter h = e0 >> 9 of the 2N-periodic extension:
+                    //   (rot_lo, rot_hi) = h0:(lo,hi) h1:(hi,-lo) h2:(-lo,-hi) h3:(-hi,lo)
+                    // swap on bit 9, negate rot_lo on bit 10, rot_hi on bit 9 ^ bit 10.  ncu showed this integer glue at
+                    // 19 % of the kernel's issue slots (55 instructions per point with 64-bit selects, negations and
+                    // compares); only the high word of each difference is needed for the one-level digit.
+                    const bool sw = (e0 & 512) != 0;
+                    const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
+                    const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
+                    const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
+                    const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
+                    v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
+                                digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
                 }
                 PROF_MARK(0);  // build
                 cplx *s = flip ? scr1 : scr0;
@@ -1070,6 +1105,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
         }
     };
     if (producer) produce(0);
+    __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
     int want = -1;  // next ring refill the producer owes (issued one barrier into the following transform)
 
     const cplx *t2s = t2tab + (t & 7);
@@ -1149,6 +1185,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
                 produce(want);
                 want = -1;
             }
+            __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
             fwd_p2_s(v, scr, t2s, t);
             group_sync(sbar);
             fwd_p3(v, scr, t);
@@ -1191,6 +1228,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
                 produce(want);
                 want = -1;
             }
+            __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
             inv_p2_s(acc[c], scr, t2s, t);
             group_sync(sbar);
             inv_p1(acc[c], scr, tw, t);
@@ -1408,6 +1446,7 @@ __global__ void __launch_bounds__(64 * kSsGroups, 1) k_scheme_switch_v2(const ui
     };
     if (producer)
         for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, tile_src(b), kBrTileBytes, full + b);
+    __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
     int tile = 0;
     unsigned char *base = smem_raw + (size_t)gi * kSsGroupSmem;
     uint64_t *gl = reinterpret_cast<uint64_t *>(base);
@@ -1450,6 +1489,7 @@ __global__ void __launch_bounds__(64 * kSsGroups, 1) k_scheme_switch_v2(const ui
                     mbar_wait(empty + pb, puse & 1);
                     tma_load_tile(ring + pb * kBrTileBytes, tile_src(tile - 1 + kBrRing), kBrTileBytes, full + pb);
                 }
+                __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
                 cplx v[8];
 #pragma unroll
                 for (int m = 0; m < 8; m++)
@@ -1762,6 +1802,7 @@ __global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8_v2(const double *__
     };
     if (producer)
         for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, tile_src(b), kBrTileBytes, full + b);
+    __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
 
     unsigned char *base = smem_raw + (size_t)gi * kLut2GroupSmem;
     uint64_t *acc = reinterpret_cast<uint64_t *>(base);
@@ -1809,6 +1850,7 @@ __global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8_v2(const double *__
                     mbar_wait(empty + pb, puse & 1);
                     tma_load_tile(ring + pb * kBrTileBytes, tile_src(tile - 1 + kBrRing), kBrTileBytes, full + pb);
                 }
+                __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
                 if (!zero) {
                     cplx v[8];
 #pragma unroll

@@ -269,6 +269,10 @@ CBS_HD int32_t decomp_next(uint64_t &st, int base_log)
     return (int32_t)(uint32_t)(res - (carry << base_log));
 }
 
+// tfhe SignedDecomposer(base_log 23, level 1) digit of a 64-bit word from its high 32 bits alone:
+//   s = ((hi >> 8) + 1) >> 1, digit = s - (s > 2^22 ? 2^23 : 0)  ==  (((int32)(hi - 0x100)) >> 9) + 1
+CBS_HD int32_t digit_b23_l1_hi(uint32_t hi) { return (((int32_t)(hi - 0x100u)) >> 9) + 1; }
+
 // exact int32 -> double without the conversion pipe (|x| < 2^31)
 CBS_HD double i32_to_double(int32_t x)
 {

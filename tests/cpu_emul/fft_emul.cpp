@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <initializer_list>
 #include <cmath>
 #include "fft_tables.h"
 using namespace cbs;
@@ -193,6 +194,12 @@ int main()
             int nr = 64 - bl[cfg] * lv[cfg];
             uint64_t closest = ((x >> nr) + ((x >> (nr - 1)) & 1)) << nr;
             if (r != closest) bad_dec++;
+        }
+        // the blind rotation's one-level digit from the high word only
+        for (uint64_t y : std::initializer_list<uint64_t>{x, x | 0xffffff0000000000ull, x & 0x000000ffffffffffull, (x & 0xffffffffffull) | 0x7fffff0000000000ull,
+                           (x & 0xffffffffffull) | 0x8000000000000000ull, (x & 0xffffffffffull) | 0x7fffff8000000000ull}) {
+            uint64_t st = decomp_init(y, 23, 1);
+            if (decomp_next(st, 23) != digit_b23_l1_hi((uint32_t)(y >> 32))) bad_dec++;
         }
     }
     int bad_tor = 0;
