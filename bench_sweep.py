@@ -24,6 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cbs-only", action="store_true")
     ap.add_argument("--aes-only", action="store_true")
+    ap.add_argument("--mini", action="store_true", help="also run the mini-workload sweep when --cbs-only/--aes-only is given")
     ap.add_argument("--max-batch", type=int, default=16384)
     ap.add_argument("--aes-blocks", type=int, nargs="*", default=[1, 8, 64, 256, 1024])
     ap.add_argument("--out", default=None)
@@ -100,6 +101,26 @@ def main():
             emit({"bench": "aes128_transcipher", "blocks": nb, "ms": ms, "blocks_per_s": nb / (ms * 1e-3),
                   "cbs_per_s": nb * 1152 / (ms * 1e-3), "verified": bool(ok), "noise_log2_std": std, "noise_log2_max": mx,
                   "n_gpus": 1})
+    if not args.cbs_only and not args.aes_only or args.mini:
+        # mini-workloads of the three harness instances (workload_specification.md:8-9): max and inner product mod 2^16
+        # over 8 / 64 / 512 u16 values given as bit ciphertexts; host buffers through the C ABI, second (warm) call timed
+        for nvals in (8, 64, 512):
+            vals = np.random.default_rng(nvals).integers(0, 65536, nvals).tolist()
+            bits = np.array([(v >> (15 - i)) & 1 for v in vals for i in range(16)], dtype=np.uint8)
+            lwe = ks.encrypt_bits_big(bits, 7 + nvals)
+            for name, fn, want in (("max_u16", ctx.max_u16, max(vals)),
+                                   ("inner_product_u16", ctx.inner_product_u16,
+                                    sum((x * y) % 65536 for x, y in zip(vals[: nvals // 2], vals[nvals // 2:])) % 65536)):
+                fn(lwe)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                got_ct = fn(lwe)
+                dt = time.perf_counter() - t0
+                got = ref_io.bits_to_u16(ref_io.decode_bit(ref_io.lwe_phase(got_ct, ks.glwe_sk)))[0]
+                d = {"bench": name, "values": nvals, "seconds": dt, "verified": bool(got == want), "n_gpus": 1}
+                if name == "inner_product_u16":
+                    _, d["circuit_bootstraps"], d["layers"], d["lut_ladders"] = cbs.inner_product_plan_check(np.array(vals, dtype=np.uint16))
+                emit(d)
     if args.out:
         with open(args.out, "w") as f:
             for d in lines:

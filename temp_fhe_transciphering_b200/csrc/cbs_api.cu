@@ -937,15 +937,18 @@ int cbs_max_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
         return CBS_OK;
     }
     // balanced tree: level buffers A (current) and B (next)
-    uint64_t *d_lwe[2], *d_ks;
+    uint64_t *d_lwe[2], *d_op[2], *d_ks, *d_glev;
     double *d_ggsw[2];
     int *d_a, *d_b;
-    const size_t vals_lwe = (size_t)16 * kLweBig, vals_ggsw = (size_t)16 * kGgswWords;
+    const size_t vals_lwe = (size_t)16 * kLweBig, vals_ggsw = (size_t)16 * kGgswWords, vals_op = (size_t)16 * kGlweWords;
     TRY(ws_typed(ctx, "max_lwe0", (size_t)nvals * vals_lwe, &d_lwe[0]));
     TRY(ws_typed(ctx, "max_lwe1", (size_t)((nvals + 1) / 2) * vals_lwe, &d_lwe[1]));
     TRY(ws_typed(ctx, "max_ggsw0", (size_t)nvals * vals_ggsw, &d_ggsw[0]));
     TRY(ws_typed(ctx, "max_ggsw1", (size_t)((nvals + 1) / 2) * vals_ggsw, &d_ggsw[1]));
+    TRY(ws_typed(ctx, "max_op0", (size_t)nvals * vals_op, &d_op[0]));
+    TRY(ws_typed(ctx, "max_op1", (size_t)((nvals + 1) / 2) * vals_op, &d_op[1]));
     TRY(ws_typed(ctx, "ks", (size_t)nvals * 16 * kLweSmall, &d_ks));
+    TRY(ws_typed(ctx, "glev", (size_t)nvals * 16 * kGlevWords, &d_glev));  // the circuit bootstrap's own GLEV workspace
     TRY(ws_typed(ctx, "max_a", (size_t)nvals, &d_a));
     TRY(ws_typed(ctx, "max_b", (size_t)nvals, &d_b));
     std::vector<int> ha(nvals / 2), hb(nvals / 2);
@@ -958,19 +961,25 @@ int cbs_max_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
     TRY(upload(ctx, d_lwe[0], in, (size_t)nvals * vals_lwe * 8));
     int cnt = nvals, cur = 0, fresh = nvals;  // `fresh` leading values of the current level still need a CBS
     while (cnt > 1) {
-        // keyswitch + circuit bootstrap the values produced by the previous level (server_encrypted_compute.rs:213-263,314-342)
+        // keyswitch + circuit bootstrap the values produced by the previous level (server_encrypted_compute.rs:213-263,314-342);
+        // the level-1 GLEV of the same bootstrap, doubled, is the refreshed data operand of the ladder
         TRY(dev_keyswitch(ctx, d_lwe[cur], d_ks, fresh * 16));
         TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw[cur], fresh * 16));
+        launch_glev_to_operand(d_glev, d_op[cur], fresh * 16, ctx->stream);
+        ctx->launches++;
+        TRY(check_launch("k_glev_to_operand"));
         const int npairs = cnt / 2;
-        launch_max_ladder(ctx->K, d_ggsw[cur], d_lwe[cur], d_a, d_b, d_lwe[cur ^ 1], npairs, ctx->stream);
+        launch_max_ladder(ctx->K, d_ggsw[cur], d_op[cur], d_a, d_b, d_lwe[cur ^ 1], npairs, ctx->stream);
         ctx->launches++;
         TRY(check_launch("k_max_ladder"));
         int next = npairs;
-        if (cnt & 1) {  // odd one out is carried with its GGSW (no new bootstrap needed)
+        if (cnt & 1) {  // odd one out is carried with its GGSW and operand (no new bootstrap needed)
             CUDA_TRY(cudaMemcpyAsync(d_lwe[cur ^ 1] + (size_t)npairs * vals_lwe, d_lwe[cur] + (size_t)(cnt - 1) * vals_lwe,
                                      vals_lwe * 8, cudaMemcpyDeviceToDevice, ctx->stream));
             CUDA_TRY(cudaMemcpyAsync(d_ggsw[cur ^ 1] + (size_t)npairs * vals_ggsw, d_ggsw[cur] + (size_t)(cnt - 1) * vals_ggsw,
                                      vals_ggsw * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(d_op[cur ^ 1] + (size_t)npairs * vals_op, d_op[cur] + (size_t)(cnt - 1) * vals_op,
+                                     vals_op * 8, cudaMemcpyDeviceToDevice, ctx->stream));
             next++;
         }
         fresh = npairs;

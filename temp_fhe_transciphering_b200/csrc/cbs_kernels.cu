@@ -2055,22 +2055,34 @@ void launch_reverse_bits(const uint64_t *in, uint64_t *out, int nblocks, cudaStr
 //   e <- lwe_a[j] (const-embedded);  for i = 15..0 (LSB -> MSB):
 //     m0 = e + Gb[i] (x) (A - e);  m1 = B + Gb[i] (x) (e - B);  e = m0 + Ga[i] (x) (m1 - m0)
 //   with A = embed(lwe_b[j]), B = embed(lwe_a[j]) (the reference's naming is crossed, :78-79).
-// Differences from the reference, both deliberate: e starts from operand a's bit instead
+// Differences from the reference, all deliberate: e starts from operand a's bit instead
 // of carrying the previous output bit's e, so output bits are independent (parallel) and a == b
-// yields the right value instead of a stale one.
+// yields the right value instead of a stale one; and the data operands A, B are not the const-embedded input
+// LWEs but FRESH encryptions of the same bits taken from the circuit bootstrap that is run anyway for the selector
+// GGSWs: 2 x (level-1 GLEV ciphertext, which encrypts bit * 2^62 after the trace).  With the raw LWEs the data
+// noise is carried from one max_of_two to the next and grows with the depth of the reduction (measured 2^58.5
+// after 3 levels, 2^60.2 after 9: the 512-value maximum of the medium instance came out wrong); refreshed
+// operands make every level's output noise independent of the levels below.
 constexpr int kMaxGroups = 2;
 constexpr int kMaxGroupSmem = 3 * kGlweWords * 8 + 2 * 512 * 16;  // e, m0, m1 + tiles = 88 KB
 constexpr int kMaxSmemBytes = kMaxGroups * kMaxGroupSmem;
 
-__device__ __forceinline__ uint64_t embed_word(const uint64_t *lwe, int p, int j)
+// operand GLWEs of the ladder: op[i] = 2 * glev[i][level 1]  (bit * 2^63 in the constant coefficient)
+__global__ void k_glev_to_operand(const uint64_t *__restrict__ glev, uint64_t *__restrict__ op)
 {
-    // convert_lwe_to_glwe_const, cbs_lib/src/glwe_conv.rs:12-44
-    if (p < 2) return (j == 0) ? lwe[p * 1024] : (0ull - lwe[p * 1024 + 1024 - j]);
-    return (j == 0) ? lwe[2048] : 0ull;
+    const uint64_t *src = glev + (size_t)blockIdx.x * kGlevWords;
+    uint64_t *dst = op + (size_t)blockIdx.x * kGlweWords;
+    for (int w = threadIdx.x; w < kGlweWords; w += blockDim.x) dst[w] = src[w] << 1;
+}
+
+void launch_glev_to_operand(const uint64_t *glev, uint64_t *op, int count, cudaStream_t s)
+{
+    if (count <= 0) return;
+    k_glev_to_operand<<<count, 256, 0, s>>>(glev, op);
 }
 
 __global__ void __launch_bounds__(64 * kMaxGroups, 1) k_max_ladder(const double *__restrict__ ggsw_f,
-                                                                    const uint64_t *__restrict__ lwe,
+                                                                    const uint64_t *__restrict__ op,
                                                                     const int *__restrict__ a_idx,
                                                                     const int *__restrict__ b_idx,
                                                                     uint64_t *__restrict__ out, int npairs,
@@ -2094,9 +2106,9 @@ __global__ void __launch_bounds__(64 * kMaxGroups, 1) k_max_ladder(const double 
     load_twiddles(tw, twtab, g.t);
     const int t = g.t;
     const int va = a_idx[pair], vb = b_idx[pair];
-    const uint64_t *la = lwe + ((size_t)va * 16 + jbit) * kLweBig;  // operand a, bit j  -> "B"
-    const uint64_t *lb = lwe + ((size_t)vb * 16 + jbit) * kLweBig;  // operand b, bit j  -> "A"
-    for (int w = t; w < kGlweWords; w += 64) e[w] = embed_word(la, w >> 10, w & 1023);
+    const uint64_t *la = op + ((size_t)va * 16 + jbit) * kGlweWords;  // operand a, bit j  -> "B"
+    const uint64_t *lb = op + ((size_t)vb * 16 + jbit) * kGlweWords;  // operand b, bit j  -> "A"
+    for (int w = t; w < kGlweWords; w += 64) e[w] = la[w];
     group_sync(g.bar);
     cplx o[3][8];
 #pragma unroll 1
@@ -2104,7 +2116,7 @@ __global__ void __launch_bounds__(64 * kMaxGroups, 1) k_max_ladder(const double 
         const double *Ga = ggsw_f + ((size_t)va * 16 + i) * kGgswWords;
         const double *Gb = ggsw_f + ((size_t)vb * 16 + i) * kGgswWords;
         // m0 = e + Gb (x) (A - e)
-        cbs_external_product(o, Gb, g, tw, [&](int r, int j) { return embed_word(lb, r, j) - e[r * 1024 + j]; });
+        cbs_external_product(o, Gb, g, tw, [&](int r, int j) { return lb[r * 1024 + j] - e[r * 1024 + j]; });
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             inv_fft(o[c], g, tw);
@@ -2116,15 +2128,15 @@ __global__ void __launch_bounds__(64 * kMaxGroups, 1) k_max_ladder(const double 
             }
         }
         // m1 = B + Gb (x) (e - B)
-        cbs_external_product(o, Gb, g, tw, [&](int r, int j) { return e[r * 1024 + j] - embed_word(la, r, j); });
+        cbs_external_product(o, Gb, g, tw, [&](int r, int j) { return e[r * 1024 + j] - la[r * 1024 + j]; });
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             inv_fft(o[c], g, tw);
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 const int j = t + 64 * m;
-                m1[c * 1024 + j] = embed_word(la, c, j) + torus_from_scaled(o[c][m].x);
-                m1[c * 1024 + j + 512] = embed_word(la, c, j + 512) + torus_from_scaled(o[c][m].y);
+                m1[c * 1024 + j] = la[c * 1024 + j] + torus_from_scaled(o[c][m].x);
+                m1[c * 1024 + j + 512] = la[c * 1024 + j + 512] + torus_from_scaled(o[c][m].y);
             }
         }
         // e = m0 + Ga (x) (m1 - m0)   (only own coefficients are touched: no cross-thread hazard)
@@ -2150,7 +2162,7 @@ __global__ void __launch_bounds__(64 * kMaxGroups, 1) k_max_ladder(const double 
     if (t == 0) dst[2048] = e[2048];
 }
 
-void launch_max_ladder(const DeviceKeys &K, const double *ggsw_f, const uint64_t *lwe, const int *a_idx,
+void launch_max_ladder(const DeviceKeys &K, const double *ggsw_f, const uint64_t *op, const int *a_idx,
                        const int *b_idx, uint64_t *out, int npairs, cudaStream_t s)
 {
     if (npairs <= 0) return;
@@ -2163,7 +2175,7 @@ void launch_max_ladder(const DeviceKeys &K, const double *ggsw_f, const uint64_t
         attr = true;
     }
     const int groups = npairs * 16;
-    k_max_ladder<<<(groups + kMaxGroups - 1) / kMaxGroups, 64 * kMaxGroups, kMaxSmemBytes, s>>>(ggsw_f, lwe, a_idx, b_idx,
+    k_max_ladder<<<(groups + kMaxGroups - 1) / kMaxGroups, 64 * kMaxGroups, kMaxSmemBytes, s>>>(ggsw_f, op, a_idx, b_idx,
                                                                                                   out, npairs, K.tw);
 }
 

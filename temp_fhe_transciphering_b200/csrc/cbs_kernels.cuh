@@ -87,9 +87,11 @@ void launch_reverse_bits(const uint64_t *in, uint64_t *out, int nblocks, cudaStr
 
 // a10 CMux ladder of max_of_two for `npairs` independent pairs of 16-bit values.
 //     ggsw_f: Fourier GGSW of every value's 16 bits (MSB first); a_idx/b_idx: value indices;
-//     lwe: the values' LWE(2048) bits [nvalues][16][2049]; out[npairs][16][2049].
-void launch_max_ladder(const DeviceKeys &K, const double *ggsw_f, const uint64_t *lwe, const int *a_idx,
+//     op: the values' bits as fresh GLWE operands [nvalues][16][3072] (launch_glev_to_operand); out[npairs][16][2049].
+void launch_max_ladder(const DeviceKeys &K, const double *ggsw_f, const uint64_t *op, const int *a_idx,
                        const int *b_idx, uint64_t *out, int npairs, cudaStream_t s);
+// op[i] = 2 * glev[i][level 1]: a fresh GLWE encryption of bit i at 2^63 from its circuit bootstrap's GLEV
+void launch_glev_to_operand(const uint64_t *glev, uint64_t *op, int count, cudaStream_t s);
 
 // FP64 FMA throughput probe: blocks x 256 threads x iters x 16 FMAs
 void launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s);

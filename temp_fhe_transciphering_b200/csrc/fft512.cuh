@@ -62,6 +62,9 @@ CBS_HD void cfma(cplx &acc, cplx a, cplx b)
                    0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913}
 
 // 8-point DFT, natural order in and out.  INV = false: W = exp(-2*pi*i/8); true: exp(+2*pi*i/8).
+// The two odd eighth roots (+-1 +- i)/sqrt2 are applied WITHOUT their 1/sqrt2 in stage 1; the factor is folded
+// into the last stage as fused multiply-adds (8 DFMA replace 8 DADD + 4 DMUL: the FP64 pipe is the unit
+// these kernels keep busiest).
 template <bool INV>
 CBS_HD void dft8(cplx v[8])
 {
@@ -70,21 +73,21 @@ CBS_HD void dft8(cplx v[8])
     cplx b1 = cadd(v[1], v[5]), d1 = csub(v[1], v[5]);
     cplx b2 = cadd(v[2], v[6]), d2 = csub(v[2], v[6]);
     cplx b3 = cadd(v[3], v[7]), d3 = csub(v[3], v[7]);
-    cplx b5, b6, b7;
+    cplx b5, b6, b7;  // b5, b7 are sqrt2 times the true values
     if (!INV) {
-        b5 = {(d1.x + d1.y) * kSqrtHalf, (d1.y - d1.x) * kSqrtHalf};   // * (1 - i)/sqrt2
-        b6 = {d2.y, -d2.x};                                            // * (-i)
-        b7 = {(d3.y - d3.x) * kSqrtHalf, -(d3.x + d3.y) * kSqrtHalf};  // * (-1 - i)/sqrt2
+        b5 = {d1.x + d1.y, d1.y - d1.x};     // * (1 - i)
+        b6 = {d2.y, -d2.x};                  // * (-i)
+        b7 = {d3.y - d3.x, -(d3.x + d3.y)};  // * (-1 - i)
     } else {
-        b5 = {(d1.x - d1.y) * kSqrtHalf, (d1.x + d1.y) * kSqrtHalf};   // * (1 + i)/sqrt2
-        b6 = {-d2.y, d2.x};                                            // * (+i)
-        b7 = {-(d3.x + d3.y) * kSqrtHalf, (d3.x - d3.y) * kSqrtHalf};  // * (-1 + i)/sqrt2
+        b5 = {d1.x - d1.y, d1.x + d1.y};     // * (1 + i)
+        b6 = {-d2.y, d2.x};                  // * (+i)
+        b7 = {-(d3.x + d3.y), d3.x - d3.y};  // * (-1 + i)
     }
     // stage 2 (two 4-point DFTs)
     cplx c0 = cadd(b0, b2), c2 = csub(b0, b2);
     cplx c1 = cadd(b1, b3), e3 = csub(b1, b3);
     cplx c4 = cadd(b4, b6), c6 = csub(b4, b6);
-    cplx c5 = cadd(b5, b7), e7 = csub(b5, b7);
+    cplx c5 = cadd(b5, b7), e7 = csub(b5, b7);  // sqrt2 times the true values
     cplx c3, c7;
     if (!INV) {
         c3 = {e3.y, -e3.x};
@@ -98,10 +101,10 @@ CBS_HD void dft8(cplx v[8])
     v[4] = csub(c0, c1);
     v[2] = cadd(c2, c3);
     v[6] = csub(c2, c3);
-    v[1] = cadd(c4, c5);
-    v[5] = csub(c4, c5);
-    v[3] = cadd(c6, c7);
-    v[7] = csub(c6, c7);
+    v[1] = {c4.x + kSqrtHalf * c5.x, c4.y + kSqrtHalf * c5.y};
+    v[5] = {c4.x - kSqrtHalf * c5.x, c4.y - kSqrtHalf * c5.y};
+    v[3] = {c6.x + kSqrtHalf * c7.x, c6.y + kSqrtHalf * c7.y};
+    v[7] = {c6.x - kSqrtHalf * c7.x, c6.y - kSqrtHalf * c7.y};
 }
 
 // physical slot of logical (k1, a, b): position a + 8*b inside block k1, XOR-swizzled

@@ -212,6 +212,16 @@ def test_max_u16(ctx, keyset):
     dec, std, mx = ref_io.noise_stats(got, keyset.glwe_sk)
     assert ref_io.bits_to_u16(dec) == [max(vals)]
     assert mx < 61.5
+    # deeper reduction trees (odd counts exercise the carried value): the data operands of every level are refreshed
+    # from the circuit bootstrap, so the output noise must not grow with the depth (it did with the raw LWE operands:
+    # 2^58.5 after 3 levels, 2^60.2 after 9, and the 512-value maximum came out wrong)
+    for n in (33, 200):
+        vals = np.random.default_rng(n).integers(0, 65536, n).tolist()
+        bits = np.array([(v >> (15 - i)) & 1 for v in vals for i in range(16)], dtype=np.uint8)
+        got = ctx.max_u16(keyset.encrypt_bits_big(bits, n))
+        dec, std, mx = ref_io.noise_stats(got, keyset.glwe_sk)
+        assert ref_io.bits_to_u16(dec) == [max(vals)], n
+        assert mx < 61.5, (n, std, mx)
 
 
 def test_inner_product_u16(ctx, keyset):
