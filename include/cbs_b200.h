@@ -177,6 +177,14 @@ int cbs_aes128_ctr_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, con
  * (sequential fold); any nvals >= 1 is reduced as a balanced tree here. */
 int cbs_max_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out);
 
+/* The same maximum as a LUT circuit (csrc/host/ip_plan.h max_make_plan: nibble comparators, one select ladder per output
+ * bit, fresh operands; 55 circuit bootstraps per max_of_two, two bootstrap layers per tree level).  Its output noise
+ * (2^58) depends neither on the data nor on the tree depth; cbs_max_u16 switches to it above the reference's 8 values
+ * (CBS_MAX_VARIANT=ladder|lut overrides).  cbs_max_plan_check dry-runs the plan on cleartext values (host only). */
+int cbs_max_u16_lut(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out);
+int cbs_max_plan_check(const uint16_t *vals, int nvals, uint16_t *result, int64_t *circuit_bootstraps, int *layers,
+                       int64_t *lut_ladders);
+
 /* Mini-workload #2 of the harness (harness/cleartext_impl.py:65-70, README.md:43; the reference submission has
  * no implementation): encrypted  sum_i (x_i * y_i mod 2^16) mod 2^16  with x = the first nvals/2 values and
  * y = the second half; in[nvals][16] big LWE (MSB first, the payload of ciphertext_aes_download/result.bin)

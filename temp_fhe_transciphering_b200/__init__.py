@@ -79,6 +79,18 @@ def inner_product_plan_check(vals):
     return int(res.value), int(ncbs.value), int(layers.value), int(ladders.value)
 
 
+def max_plan_check(vals):
+    """Host-only dry run of the LUT-circuit maximum on cleartext u16 values -> (result, circuit bootstraps, layers, ladders)."""
+    v = np.ascontiguousarray(vals, dtype=np.uint16)
+    res = ctypes.c_uint16()
+    ncbs = ctypes.c_int64()
+    layers = ctypes.c_int()
+    ladders = ctypes.c_int64()
+    _check(lib().cbs_max_plan_check(v.ctypes.data_as(ctypes.c_void_p), int(v.size), ctypes.byref(res), ctypes.byref(ncbs),
+                                    ctypes.byref(layers), ctypes.byref(ladders)), "cbs_max_plan_check")
+    return int(res.value), int(ncbs.value), int(layers.value), int(ladders.value)
+
+
 def _check(rc, what):
     if rc != 0:
         raise CbsError(f"{what} failed (code {rc}): {lib().cbs_last_error().decode()}")
@@ -391,6 +403,14 @@ class Context:
         nvals = a.shape[0] // 16
         out, po = _out((16, LWE_BIG))
         _check(lib().cbs_max_u16(self._h, pi, nvals, po), "cbs_max_u16")
+        return out
+
+    def max_u16_lut(self, lwe_bits):
+        """the maximum as a LUT circuit (noise independent of data and tree depth); same formats as max_u16."""
+        a, pi = _u64(np.reshape(lwe_bits, (-1, LWE_BIG)))
+        nvals = a.shape[0] // 16
+        out, po = _out((16, LWE_BIG))
+        _check(lib().cbs_max_u16_lut(self._h, pi, nvals, po), "cbs_max_u16_lut")
         return out
 
     def inner_product_u16(self, lwe_bits):

@@ -395,6 +395,8 @@ int dev_transcipher(cbs_ctx *ctx, const uint8_t *d_ct, int nblocks, uint64_t *d_
 
 }  // namespace
 
+static int run_lut_plan(cbs_ctx *ctx, const cbs_host::IpPlan &plan, const uint64_t *in, uint64_t *out);
+
 extern "C" {
 
 int cbs_device_count(int *count)
@@ -936,6 +938,13 @@ int cbs_max_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
         memcpy(out, in, (size_t)16 * kLweBig * 8);
         return CBS_OK;
     }
+    // up to the reference's own 8 values: its max_of_two CMux ladder; above (where the reference cannot run and the
+    // ladder's data-dependent noise becomes a real failure probability): the LUT circuit.  CBS_MAX_VARIANT=ladder|lut overrides.
+    {
+        const char *e = getenv("CBS_MAX_VARIANT");
+        const bool lut = e ? (strcmp(e, "lut") == 0) : nvals > 8;
+        if (lut) return run_lut_plan(ctx, cbs_host::max_make_plan(nvals), in, out);
+    }
     // balanced tree: level buffers A (current) and B (next)
     uint64_t *d_lwe[2], *d_op[2], *d_ks, *d_glev;
     double *d_ggsw[2];
@@ -989,33 +998,40 @@ int cbs_max_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
     return download(ctx, out, d_lwe[cur], vals_lwe * 8);
 }
 
-// Mini-workload #2 of the harness (harness/cleartext_impl.py:65-70; no reference implementation exists, SURVEY.md
-// 8(f)2): sum_i (x_i * y_i mod 2^16) mod 2^16 with x = first half, y = second half of the values.  The circuit
-// (nibble products, column compression by population counts, nibble adders) is planned on the host by
-// host/ip_plan.h; every layer is [gather -> LWE keyswitch -> circuit bootstrap -> gathered LUT ladders].
-int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
-{
-    ENTER(ctx);
-    if (nvals <= 0 || (nvals & 1) || !in || !out) return set_error("cbs_inner_product_u16: bad argument (need an even number of values)"), CBS_ERR_ARG;
-    using namespace cbs_host;
-    const IpPlan plan = ip_make_plan(nvals);
-    constexpr int kCap = 8192;  // circuit bootstraps per sub-batch (bounds the Fourier GGSW workspace to 4.2 GB)
+}  // extern "C"
 
-    // flatten the plan into sub-batches of jobs whose selectors fit the cap
+// Executes a host-planned LUT circuit (host/ip_plan.h) on `nin` input bit ciphertexts: every layer is
+// [LWE additions] -> [gather -> LWE keyswitch -> circuit bootstrap] -> [fresh operands from the bootstrap's GLEV] ->
+// [gathered LUT ladders] -> [LWE additions]; layers whose bootstraps exceed the workspace cap run in sub-batches.
+static int run_lut_plan(cbs_ctx *ctx, const cbs_host::IpPlan &plan, const uint64_t *in, uint64_t *out)
+{
+    using namespace cbs_host;
+    constexpr int kCap = 8192;  // circuit bootstraps per sub-batch (bounds the Fourier GGSW workspace to 4.2 GB)
     struct Batch {
-        int idx_off, m, job_off, njobs;
+        int idx_off, m, job_off, njobs, ref_off, nref;
     };
-    std::vector<Batch> batches;
-    std::vector<int> h_idx, h_sel, h_lut, h_out;
+    struct LayerExec {
+        int pre_off, npre, post_off, npost;
+        std::vector<Batch> batches;
+    };
+    std::vector<LayerExec> layers;
+    std::vector<int> h_idx, h_sel, h_lut, h_out, h_add, h_ref;
     for (const IpLayer &L : plan.layers) {
-        std::vector<int> remap(L.cbs.size(), -1);
-        std::vector<int> touched;
-        Batch b{(int)h_idx.size(), 0, (int)h_lut.size(), 0};
+        LayerExec E;
+        E.pre_off = (int)h_add.size() / 3;
+        E.npre = (int)L.pre.size();
+        for (const IpAdd &a : L.pre) h_add.insert(h_add.end(), {a.dst, a.a, a.b});
+        E.post_off = (int)h_add.size() / 3;
+        E.npost = (int)L.post.size();
+        for (const IpAdd &a : L.post) h_add.insert(h_add.end(), {a.dst, a.a, a.b});
+        std::vector<int> remap(L.cbs.size(), -1), ref_dst(L.cbs.size(), -1), touched;
+        for (const IpRefresh &r : L.refresh) ref_dst[(size_t)r.pos] = r.dst;
+        Batch b{(int)h_idx.size(), 0, (int)h_lut.size(), 0, (int)h_ref.size() / 2, 0};
         auto flush = [&]() {
-            if (b.njobs) batches.push_back(b);
+            if (b.njobs) E.batches.push_back(b);
             for (int pos : touched) remap[(size_t)pos] = -1;
             touched.clear();
-            b = Batch{(int)h_idx.size(), 0, (int)h_lut.size(), 0};
+            b = Batch{(int)h_idx.size(), 0, (int)h_lut.size(), 0, (int)h_ref.size() / 2, 0};
         };
         for (const IpJob &j : L.jobs) {
             int fresh = 0;
@@ -1030,6 +1046,10 @@ int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t 
                         r = b.m++;
                         touched.push_back(j.sel[i]);
                         h_idx.push_back(L.cbs[(size_t)j.sel[i]]);
+                        if (ref_dst[(size_t)j.sel[i]] >= 0) {
+                            h_ref.insert(h_ref.end(), {r, ref_dst[(size_t)j.sel[i]]});
+                            b.nref++;
+                        }
                     }
                     v = r;
                 }
@@ -1040,9 +1060,11 @@ int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t 
             b.njobs++;
         }
         flush();
+        layers.push_back(std::move(E));
     }
     int max_m = 1;
-    for (const Batch &b : batches) max_m = b.m > max_m ? b.m : max_m;
+    for (const LayerExec &E : layers)
+        for (const Batch &b : E.batches) max_m = b.m > max_m ? b.m : max_m;
     for (int i = 0; i < 16; i++) h_idx.push_back(plan.result[15 - i]);  // final gather, MSB first
 
     // trivial LUT accumulators: coefficient i carries bit (4*acc + i/256) of table[i % 256] at 2^63
@@ -1054,19 +1076,22 @@ int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t 
             for (int i = 0; i < 1024; i++) body[i] = (uint64_t)((ip_lut_value(l, (unsigned)(i % 256)) >> (4 * a + i / 256)) & 1u) << 63;
         }
 
-    uint64_t *d_pool, *d_rows, *d_ks, *d_luts;
+    uint64_t *d_pool, *d_rows, *d_ks, *d_luts, *d_glev;
     double *d_ggsw_f;
-    int *d_idx, *d_sel, *d_lut, *d_out;
+    int *d_idx, *d_sel, *d_lut, *d_out, *d_add, *d_ref;
     TRY(ws_typed(ctx, "ip_pool", (size_t)plan.pool_size * kLweBig, &d_pool));
     TRY(ws_typed(ctx, "ip_rows", (size_t)max_m * kLweBig, &d_rows));
     TRY(ws_typed(ctx, "ks", (size_t)max_m * kLweSmall, &d_ks));
     TRY(ws_typed(ctx, "ggsw_f", (size_t)max_m * kGgswWords, &d_ggsw_f));
+    TRY(ws_typed(ctx, "glev", (size_t)max_m * kGlevWords, &d_glev));  // the circuit bootstrap's own GLEV workspace
     TRY(ws_typed(ctx, "ip_luts", h_luts.size(), &d_luts));
     TRY(ws_typed(ctx, "ip_idx", h_idx.size(), &d_idx));
     TRY(ws_typed(ctx, "ip_sel", h_sel.size() + 1, &d_sel));
     TRY(ws_typed(ctx, "ip_lut", h_lut.size() + 1, &d_lut));
     TRY(ws_typed(ctx, "ip_out", h_out.size() + 1, &d_out));
-    TRY(upload(ctx, d_pool, in, (size_t)nvals * 16 * kLweBig * 8));
+    TRY(ws_typed(ctx, "ip_add", h_add.size() + 1, &d_add));
+    TRY(ws_typed(ctx, "ip_ref", h_ref.size() + 1, &d_ref));
+    TRY(upload(ctx, d_pool, in, (size_t)plan.nin_bits * kLweBig * 8));
     TRY(upload(ctx, d_luts, h_luts.data(), h_luts.size() * 8));
     TRY(upload(ctx, d_idx, h_idx.data(), h_idx.size() * sizeof(int)));
     if (!h_lut.empty()) {
@@ -1074,22 +1099,62 @@ int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t 
         TRY(upload(ctx, d_lut, h_lut.data(), h_lut.size() * sizeof(int)));
         TRY(upload(ctx, d_out, h_out.data(), h_out.size() * sizeof(int)));
     }
-    for (const Batch &b : batches) {
-        launch_gather_lwe(d_pool, d_idx + b.idx_off, d_rows, b.m, ctx->stream);
-        ctx->launches++;
-        TRY(check_launch("k_gather_lwe"));
-        TRY(dev_keyswitch(ctx, d_rows, d_ks, b.m));
-        TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, b.m));
-        launch_lut8_gather(ctx->K, d_ggsw_f, d_sel + (size_t)b.job_off * 8, d_luts, d_lut + b.job_off, d_out + b.job_off, d_pool,
-                           b.njobs, ctx->stream);
-        ctx->launches++;
-        TRY(check_launch("k_lut8_gather"));
+    if (!h_add.empty()) TRY(upload(ctx, d_add, h_add.data(), h_add.size() * sizeof(int)));
+    if (!h_ref.empty()) TRY(upload(ctx, d_ref, h_ref.data(), h_ref.size() * sizeof(int)));
+    for (const LayerExec &E : layers) {
+        if (E.npre) {
+            launch_lwe_add_rows(d_pool, d_add + (size_t)E.pre_off * 3, E.npre, ctx->stream);
+            ctx->launches++;
+            TRY(check_launch("k_lwe_add_rows"));
+        }
+        for (const Batch &b : E.batches) {
+            launch_gather_lwe(d_pool, d_idx + b.idx_off, d_rows, b.m, ctx->stream);
+            ctx->launches++;
+            TRY(check_launch("k_gather_lwe"));
+            TRY(dev_keyswitch(ctx, d_rows, d_ks, b.m));
+            TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, b.m));
+            if (b.nref) {
+                launch_glev_to_lwe(d_glev, d_ref + (size_t)b.ref_off * 2, d_pool, b.nref, ctx->stream);
+                ctx->launches++;
+                TRY(check_launch("k_glev_to_lwe"));
+            }
+            launch_lut8_gather(ctx->K, d_ggsw_f, d_sel + (size_t)b.job_off * 8, d_luts, d_lut + b.job_off, d_out + b.job_off, d_pool,
+                               b.njobs, ctx->stream);
+            ctx->launches++;
+            TRY(check_launch("k_lut8_gather"));
+        }
+        if (E.npost) {
+            launch_lwe_add_rows(d_pool, d_add + (size_t)E.post_off * 3, E.npost, ctx->stream);
+            ctx->launches++;
+            TRY(check_launch("k_lwe_add_rows"));
+        }
     }
     launch_gather_lwe(d_pool, d_idx + (h_idx.size() - 16), d_rows, 16, ctx->stream);
     ctx->launches++;
     TRY(check_launch("k_gather_lwe"));
     // download() synchronises the stream, so the host tables above outlive every asynchronous copy
     return download(ctx, out, d_rows, (size_t)16 * kLweBig * 8);
+}
+
+extern "C" {
+
+// Mini-workload #2 of the harness (harness/cleartext_impl.py:65-70; no reference implementation exists, SURVEY.md
+// 8(f)2): sum_i (x_i * y_i mod 2^16) mod 2^16 with x = first half, y = second half of the values.  The circuit
+// (nibble products, column compression by population counts, nibble adders) is planned on the host by
+// host/ip_plan.h and executed by run_lut_plan.
+int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
+{
+    ENTER(ctx);
+    if (nvals <= 0 || (nvals & 1) || !in || !out) return set_error("cbs_inner_product_u16: bad argument (need an even number of values)"), CBS_ERR_ARG;
+    return run_lut_plan(ctx, cbs_host::ip_make_plan(nvals), in, out);
+}
+
+// Maximum as a LUT circuit (host/ip_plan.h max_make_plan): noise independent of the data and of the tree depth.
+int cbs_max_u16_lut(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
+{
+    ENTER(ctx);
+    if (nvals <= 0 || !in || !out) return set_error("cbs_max_u16_lut: bad argument"), CBS_ERR_ARG;
+    return run_lut_plan(ctx, cbs_host::max_make_plan(nvals), in, out);
 }
 
 }  // extern "C"

@@ -1758,6 +1758,42 @@ void launch_gather_lwe(const uint64_t *pool, const int *idx, uint64_t *rows, int
     k_gather_lwe<<<count, 256, 0, s>>>(pool, idx, rows);
 }
 
+// pool[dst] = pool[a] + pool[b] for LWE(2048) ciphertexts (XOR of the encrypted bits at delta 2^63), triples (dst, a, b)
+__global__ void k_lwe_add_rows(uint64_t *__restrict__ pool, const int *__restrict__ triples)
+{
+    const int dst = triples[3 * blockIdx.x], a = triples[3 * blockIdx.x + 1], b = triples[3 * blockIdx.x + 2];
+    const uint64_t *pa = pool + (size_t)a * kLweBig, *pb = pool + (size_t)b * kLweBig;
+    uint64_t *o = pool + (size_t)dst * kLweBig;
+    for (int w = threadIdx.x; w < kLweBig; w += blockDim.x) o[w] = pa[w] + pb[w];
+}
+
+void launch_lwe_add_rows(uint64_t *pool, const int *triples, int count, cudaStream_t s)
+{
+    if (count <= 0) return;
+    k_lwe_add_rows<<<count, 256, 0, s>>>(pool, triples);
+}
+
+// pool[dst] = fresh LWE(2048) encryption of the bit whose circuit bootstrap left glev[pos]: 2 x the level-1 GLEV
+// ciphertext (bit * 2^62 in the constant coefficient after the trace), sample-extracted at degree 0; pairs (pos, dst)
+__global__ void k_glev_to_lwe(const uint64_t *__restrict__ glev, const int *__restrict__ pairs, uint64_t *__restrict__ pool)
+{
+    const int pos = pairs[2 * blockIdx.x], dst = pairs[2 * blockIdx.x + 1];
+    const uint64_t *g = glev + (size_t)pos * kGlevWords;
+    uint64_t *o = pool + (size_t)dst * kLweBig;
+    for (int w = threadIdx.x; w < 2048; w += blockDim.x) {
+        const int c = w >> 10, j = w & 1023;
+        const uint64_t x = (j == 0) ? g[c * 1024] : (0ull - g[c * 1024 + 1024 - j]);
+        o[w] = x << 1;
+    }
+    if (threadIdx.x == 0) o[2048] = g[2048] << 1;
+}
+
+void launch_glev_to_lwe(const uint64_t *glev, const int *pairs, uint64_t *pool, int count, cudaStream_t s)
+{
+    if (count <= 0) return;
+    k_glev_to_lwe<<<count, 256, 0, s>>>(glev, pairs, pool);
+}
+
 // ---- LUT ladder v2: GGSW row tiles staged through the same 2-deep TMA ring as the blind rotation --------
 // All groups of a CTA evaluate accumulators of the SAME byte, i.e. against the same 8 GGSW bits, so each
 // (level, row) tile of 3 Fourier polynomials is fetched once per CTA.  `groups` = jobs per CTA must divide

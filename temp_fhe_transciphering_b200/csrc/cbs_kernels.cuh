@@ -72,6 +72,11 @@ void launch_lut8_gather(const DeviceKeys &K, const double *ggsw_f, const int *se
 // rows[i] = pool[idx[i]] for LWE(2048) ciphertexts (idx < 0: trivial zero)
 void launch_gather_lwe(const uint64_t *pool, const int *idx, uint64_t *rows, int count, cudaStream_t s);
 
+// circuit plumbing (host/ip_plan.h): pool[dst] = pool[a] + pool[b] for triples (dst, a, b) of LWE(2048) rows
+void launch_lwe_add_rows(uint64_t *pool, const int *triples, int count, cudaStream_t s);
+// pool[dst] = fresh LWE(2048) of the bit bootstrapped into glev[pos] (2 x level-1 GLEV, sample 0), pairs (pos, dst)
+void launch_glev_to_lwe(const uint64_t *glev, const int *pairs, uint64_t *pool, int count, cudaStream_t s);
+
 // a8  rounds 10+9: sample extraction from the encrypted keyed LUTs (ct = raw AES ciphertext bytes; the cleartext inv_shift_rows is applied inside)
 //     luts = [nmult][16][2] GLWE, tm = [nmult][nblocks][128][2049]; inv_shift = 1 for the inverse direction
 void launch_known_rotate(const uint8_t *ct, const uint64_t *luts, uint64_t *tm, int nblocks, int nmult, int inv_shift,

@@ -25,15 +25,24 @@
 
 namespace cbs_host {
 
-// LUT tables of the plan; each yields <= 8 output bits = two accumulators of 4 bits
-enum IpLut : int { kIpMul = 0, kIpPop = 1, kIpAdd4 = 2, kIpNumLuts = 3 };
+// LUT tables of the plans; each yields <= 8 output bits = two accumulators of 4 bits
+enum IpLut : int { kIpMul = 0, kIpPop = 1, kIpAdd4 = 2, kMaxCmp = 3, kMaxSel = 4, kIpNumLuts = 5 };
 
 inline unsigned ip_lut_value(int lut, unsigned idx)
 {
     switch (lut) {
         case kIpMul: return (idx & 15u) * (idx >> 4);
         case kIpPop: return (unsigned)__builtin_popcount(idx);
-        default: return (idx & 15u) + (idx >> 4);
+        case kIpAdd4: return (idx & 15u) + (idx >> 4);
+        case kMaxCmp: {  // nibbles a = idx & 15, b = idx >> 4  ->  bit 0: a > b, bit 1: a == b
+            const unsigned a = idx & 15u, b = idx >> 4;
+            return (a > b ? 1u : 0u) | (a == b ? 2u : 0u);
+        }
+        default: {  // kMaxSel: selectors (gt0, gt1, eq1, gt2, eq2, gt3, eq3, d) -> d AND [a > b]
+            const unsigned gt0 = idx & 1, gt1 = (idx >> 1) & 1, eq1 = (idx >> 2) & 1, gt2 = (idx >> 3) & 1, eq2 = (idx >> 4) & 1,
+                           gt3 = (idx >> 5) & 1, eq3 = (idx >> 6) & 1, d = (idx >> 7) & 1;
+            return d & (gt3 | (eq3 & (gt2 | (eq2 & (gt1 | (eq1 & gt0))))));
+        }
     }
 }
 
@@ -44,16 +53,27 @@ struct IpJob {
     int out;     // pool index of the first of the 4 output bits
 };
 
+struct IpAdd {
+    int dst, a, b;  // pool[dst] = pool[a] + pool[b]  (LWE addition = XOR of the encrypted bits at delta 2^63)
+};
+struct IpRefresh {
+    int pos, dst;  // pool[dst] = a fresh encryption of the bit bootstrapped at position `pos` of this layer
+};
+
 struct IpLayer {
-    std::vector<int> cbs;  // pool indices of the bits that are keyswitched + circuit-bootstrapped in this layer
+    std::vector<IpAdd> pre;  // executed before the layer's keyswitch
+    std::vector<int> cbs;    // pool indices of the bits that are keyswitched + circuit-bootstrapped in this layer
+    std::vector<IpRefresh> refresh;  // fresh LWEs taken from the bootstrap's level-1 GLEV (2 x, sample 0)
     std::vector<IpJob> jobs;
+    std::vector<IpAdd> post;  // executed after the layer's ladders
 };
 
 struct IpPlan {
     int nvals = 0;
     int pool_size = 0;  // LWE slots: inputs first ([value][bit MSB first]), then LUT outputs
     std::vector<IpLayer> layers;
-    int result[16];  // pool index of result bit with weight 2^c, or -1 for a constant 0
+    int nin_bits = 0;   // leading pool slots holding the inputs
+    int result[16];     // pool index of result bit with weight 2^c, or -1 for a constant 0
     long total_cbs() const
     {
         long n = 0;
@@ -66,6 +86,7 @@ inline IpPlan ip_make_plan(int nvals)
 {
     IpPlan plan;
     plan.nvals = nvals;
+    plan.nin_bits = nvals * 16;
     const int P = nvals / 2;
     int pool = nvals * 16;
     std::vector<std::vector<int>> col(16);
@@ -171,13 +192,108 @@ inline IpPlan ip_make_plan(int nvals)
     return plan;
 }
 
+// Maximum of nvals 16-bit values as a LUT circuit (used above 8 values, where the reference's max_of_two CMux
+// ladder cannot run at all and its data-dependent noise - 2^60.2 under the 2^62 decoding bound when the operands share a
+// long prefix - becomes a real failure probability).  Balanced tree; one max_of_two(a, b) is two layers:
+//   layer A  bootstrap the 32 bits; 4 ladders compare the nibbles -> (a_k > b_k, a_k == b_k); the b bits are also
+//            taken back as FRESH ciphertexts from the same bootstraps (refresh);
+//   layer B  d_i = a_i xor b_i (LWE additions of the inputs); bootstrap the 7 compare bits and the 16 d_i; one ladder
+//            per output bit with selectors (gt0, gt1, eq1, gt2, eq2, gt3, eq3, d_i) -> z_i = d_i and [a > b];
+//            out_i = fresh b_i + z_i  (= b_i xor z_i): a_i if a > b, else b_i.
+// 55 bootstraps per max_of_two; every output is a fresh LUT result plus a fresh operand, so the noise (2^58) depends
+// neither on the data nor on the depth of the tree.
+inline IpPlan max_make_plan(int nvals)
+{
+    IpPlan plan;
+    plan.nvals = nvals;
+    plan.nin_bits = nvals * 16;
+    int pool = nvals * 16;
+    // a value = 16 pool indices, weight 2^w at [w]
+    std::vector<std::vector<int>> cur((size_t)nvals, std::vector<int>(16));
+    for (int v = 0; v < nvals; v++)
+        for (int w = 0; w < 16; w++) cur[(size_t)v][(size_t)w] = v * 16 + (15 - w);
+    while (cur.size() > 1) {
+        IpLayer A, B;
+        const size_t npairs = cur.size() / 2;
+        std::vector<std::vector<int>> next;
+        struct PairTmp {
+            int fresh_b[16], d[16], cmp[7];
+        };
+        std::vector<PairTmp> tmp(npairs);
+        for (size_t p = 0; p < npairs; p++) {
+            const std::vector<int> &a = cur[2 * p], &b = cur[2 * p + 1];
+            int pa[16], pb[16];
+            for (int w = 0; w < 16; w++) {
+                A.cbs.push_back(a[(size_t)w]);
+                pa[w] = (int)A.cbs.size() - 1;
+                A.cbs.push_back(b[(size_t)w]);
+                pb[w] = (int)A.cbs.size() - 1;
+                tmp[p].fresh_b[w] = pool++;
+                A.refresh.push_back(IpRefresh{pb[w], tmp[p].fresh_b[w]});
+                tmp[p].d[w] = pool++;
+                B.pre.push_back(IpAdd{tmp[p].d[w], a[(size_t)w], b[(size_t)w]});
+            }
+            for (int k = 0; k < 4; k++) {
+                IpJob j;
+                for (int i = 0; i < 4; i++) {
+                    j.sel[i] = pa[4 * k + i];
+                    j.sel[4 + i] = pb[4 * k + i];
+                }
+                j.lut = kMaxCmp;
+                j.acc = 0;
+                j.out = pool;
+                pool += 4;
+                A.jobs.push_back(j);
+                // cmp order (gt0, gt1, eq1, gt2, eq2, gt3, eq3)
+                if (k == 0) tmp[p].cmp[0] = j.out;
+                else {
+                    tmp[p].cmp[2 * k - 1] = j.out;
+                    tmp[p].cmp[2 * k] = j.out + 1;
+                }
+            }
+        }
+        for (size_t p = 0; p < npairs; p++) {
+            int pc[7];
+            for (int i = 0; i < 7; i++) {
+                B.cbs.push_back(tmp[p].cmp[i]);
+                pc[i] = (int)B.cbs.size() - 1;
+            }
+            std::vector<int> outv(16);
+            for (int w = 0; w < 16; w++) {
+                B.cbs.push_back(tmp[p].d[w]);
+                IpJob j;
+                for (int i = 0; i < 7; i++) j.sel[i] = pc[i];
+                j.sel[7] = (int)B.cbs.size() - 1;
+                j.lut = kMaxSel;
+                j.acc = 0;
+                j.out = pool;
+                pool += 4;
+                B.jobs.push_back(j);
+                const int o = pool++;
+                B.post.push_back(IpAdd{o, tmp[p].fresh_b[w], j.out});
+                outv[(size_t)w] = o;
+            }
+            next.push_back(std::move(outv));
+        }
+        if (cur.size() & 1) next.push_back(cur.back());  // odd one out passes on untouched
+        cur.swap(next);
+        plan.layers.push_back(std::move(A));
+        plan.layers.push_back(std::move(B));
+    }
+    for (int c = 0; c < 16; c++) plan.result[c] = cur[0][(size_t)c];
+    plan.pool_size = pool;
+    return plan;
+}
+
 // Run the plan on cleartext bits (tests of the circuit; nothing on the GPU path calls this).
 inline uint16_t ip_eval_clear(const IpPlan &plan, const uint16_t *vals)
 {
     std::vector<uint8_t> bit((size_t)plan.pool_size, 0);
     for (int v = 0; v < plan.nvals; v++)
         for (int w = 0; w < 16; w++) bit[(size_t)v * 16 + (15 - w)] = (vals[v] >> w) & 1;
-    for (const IpLayer &L : plan.layers)
+    for (const IpLayer &L : plan.layers) {
+        for (const IpAdd &a : L.pre) bit[(size_t)a.dst] = bit[(size_t)a.a] ^ bit[(size_t)a.b];
+        for (const IpRefresh &r : L.refresh) bit[(size_t)r.dst] = bit[(size_t)L.cbs[(size_t)r.pos]];
         for (const IpJob &j : L.jobs) {
             unsigned idx = 0;
             for (int i = 0; i < 8; i++)
@@ -185,6 +301,8 @@ inline uint16_t ip_eval_clear(const IpPlan &plan, const uint16_t *vals)
             const unsigned val = ip_lut_value(j.lut, idx) >> (4 * j.acc);
             for (int q = 0; q < 4; q++) bit[(size_t)j.out + q] = (val >> q) & 1;
         }
+        for (const IpAdd &a : L.post) bit[(size_t)a.dst] = bit[(size_t)a.a] ^ bit[(size_t)a.b];
+    }
     uint16_t r = 0;
     for (int c = 0; c < 16; c++)
         if (plan.result[c] >= 0) r |= (uint16_t)(bit[(size_t)plan.result[c]] << c);

@@ -1068,6 +1068,25 @@ int cbs_inner_product_plan_check(const uint16_t *vals, int nvals, uint16_t *resu
     return CBS_OK;
 }
 
+int cbs_max_plan_check(const uint16_t *vals, int nvals, uint16_t *result, int64_t *circuit_bootstraps, int *layers,
+                       int64_t *lut_ladders)
+{
+    if (nvals <= 0 || (!vals && result)) {
+        set_error("cbs_max_plan_check: bad argument");
+        return CBS_ERR_ARG;
+    }
+    const IpPlan plan = max_make_plan(nvals);
+    if (result) *result = ip_eval_clear(plan, vals);
+    if (circuit_bootstraps) *circuit_bootstraps = plan.total_cbs();
+    if (layers) *layers = (int)plan.layers.size();
+    if (lut_ladders) {
+        int64_t n = 0;
+        for (const IpLayer &l : plan.layers) n += (int64_t)l.jobs.size();
+        *lut_ladders = n;
+    }
+    return CBS_OK;
+}
+
 static int encrypt_bits(const uint64_t *sk, int n, double std, const uint8_t *bits, int count, uint64_t seed, uint64_t *out)
 {
     for (int c = 0; c < count; c++) {

@@ -212,16 +212,23 @@ def test_max_u16(ctx, keyset):
     dec, std, mx = ref_io.noise_stats(got, keyset.glwe_sk)
     assert ref_io.bits_to_u16(dec) == [max(vals)]
     assert mx < 61.5
-    # deeper reduction trees (odd counts exercise the carried value): the data operands of every level are refreshed
-    # from the circuit bootstrap, so the output noise must not grow with the depth (it did with the raw LWE operands:
-    # 2^58.5 after 3 levels, 2^60.2 after 9, and the 512-value maximum came out wrong)
+    # above the reference's 8 values cbs_max_u16 runs the LUT circuit (csrc/host/ip_plan.h max_make_plan): odd counts
+    # exercise the carried value, near-equal values the case where the CMux ladder's noise is largest (2^60.2)
     for n in (33, 200):
         vals = np.random.default_rng(n).integers(0, 65536, n).tolist()
+        vals[3] = max(vals) ^ 1  # a close runner-up
         bits = np.array([(v >> (15 - i)) & 1 for v in vals for i in range(16)], dtype=np.uint8)
         got = ctx.max_u16(keyset.encrypt_bits_big(bits, n))
         dec, std, mx = ref_io.noise_stats(got, keyset.glwe_sk)
         assert ref_io.bits_to_u16(dec) == [max(vals)], n
-        assert mx < 61.5, (n, std, mx)
+        assert mx < 60.5, (n, std, mx)
+    # both variants on the same 8 values
+    vals = [513, 512, 65535, 65534, 7, 7, 40000, 1]
+    bits = np.array([(v >> (15 - i)) & 1 for v in vals for i in range(16)], dtype=np.uint8)
+    lwe = keyset.encrypt_bits_big(bits, 9)
+    for fn in (ctx.max_u16, ctx.max_u16_lut):
+        dec, std, mx = ref_io.noise_stats(fn(lwe), keyset.glwe_sk)
+        assert ref_io.bits_to_u16(dec) == [65535]
 
 
 def test_inner_product_u16(ctx, keyset):

@@ -303,3 +303,19 @@ def test_inner_product_circuit_plan_matches_harness_formula(cbs):
     assert [cbs.inner_product_plan_check(np.zeros(n, np.uint16))[1:3] for n in (8, 64, 512)] == [(600, 9), (4402, 11), (34654, 13)]
     with pytest.raises(cbs.CbsError):
         cbs.inner_product_plan_check(np.zeros(3, np.uint16))
+
+
+def test_max_circuit_plan(cbs):
+    """The LUT-circuit maximum (used above 8 values), dry-run on cleartext bits: random, equal, near-equal, odd counts."""
+    rng = np.random.default_rng(6)
+    for n in (1, 2, 3, 8, 9, 64, 65, 512):
+        for trial in range(20):
+            v = rng.integers(0, 65536, n, dtype=np.uint16)
+            if trial == 0:
+                v[:] = 65535
+            if trial == 1:
+                v[:] = 0
+            if trial == 2 and n > 1:
+                v[1] = v[0] ^ 1
+            assert cbs.max_plan_check(v)[0] == int(v.max()), (n, trial)
+    assert [cbs.max_plan_check(np.zeros(n, np.uint16))[1:3] for n in (8, 64, 512)] == [(385, 6), (3465, 12), (28105, 18)]
