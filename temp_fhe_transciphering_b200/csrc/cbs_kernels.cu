@@ -773,6 +773,163 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
 // Per-step cycle budget of a v3 group (CBS_BR_PROF=1): build 4.2 k, forward passes 3.3 k, pass 3 + MAC 2.8 k,
 // inverse 4.2 k, torus + update 1.5 k, tile wait 0.5 k.
 
+// ---- low-latency blind rotation for small batches -------------------------------------------------------------
+// k_blind_rotate_v3 keeps one ciphertext per 64-thread group, so a step is a serial chain of 3 builds, 6 transforms and
+// 9 products (~15.9 k cycles, 5.8 ms per blind rotation) however few ciphertexts there are.  The toy instance (128
+// ciphertexts per round), the upper levels of the max tree and most layers of the inner-product circuit are far below
+// one wave (592), so for <= 2 ciphertexts per SM a TEAM of 192 threads owns one ciphertext: sub-group r builds and
+// transforms polynomial r, the three spectra meet in an 8 KB-per-polynomial exchange tile, sub-group c accumulates and
+// inverse-transforms output column c and updates accumulator polynomial c (which only it reads in the next build).  The
+// chain per step is 1 build + 2 transforms + 3 products.  Two teams per CTA share a 3-slot TMA ring holding the three
+// BSK row tiles of the current step; the refill for step i + 1 is issued at the top of that step.
+constexpr int kLlTeams = 2;
+constexpr int kLlTeamThreads = 192;
+constexpr int kLlTeamSmem = kGlweWords * 8 + 3 * 8192 + 3 * 8192;  // accumulator 24 KB + 3 transpose tiles + 3 exchange tiles = 72 KB
+constexpr int kLlRing = 3;
+constexpr int kLlSmemBytes = kLlTeams * kLlTeamSmem + kLlRing * kBrTileBytes + 64 + kLlTeams * kLweN * 2;
+
+__device__ __forceinline__ void named_sync(int bar, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kLlTeamThreads * kLlTeams, 1) k_blind_rotate_ll(const uint64_t *__restrict__ lwe,
+                                                                                    uint64_t *__restrict__ acc_out, int count,
+                                                                                    const double *__restrict__ bsk_f,
+                                                                                    const double *__restrict__ twtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int team = threadIdx.x / kLlTeamThreads;
+    const int u = threadIdx.x - team * kLlTeamThreads;
+    const int sub = u >> 6, t = u & 63;
+    const int ct = blockIdx.x * kLlTeams + team;
+    unsigned char *ring = smem_raw + (size_t)kLlTeams * kLlTeamSmem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kLlRing * kBrTileBytes);
+    uint64_t *empty = full + kLlRing;
+    const int active_teams = min(kLlTeams, count - blockIdx.x * kLlTeams);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kLlRing; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, kLlTeamThreads * active_teams);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (ct >= count) return;
+    const bool producer = (threadIdx.x == 0);
+    const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
+    if (producer)
+        for (int b = 0; b < kLlRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
+    __syncwarp();
+
+    unsigned char *base = smem_raw + (size_t)team * kLlTeamSmem;
+    u64x2 *acc = reinterpret_cast<u64x2 *>(base);                                     // [3][512] pairs (coef j, coef j + 512)
+    cplx *scr = reinterpret_cast<cplx *>(base + kGlweWords * 8 + sub * 8192);         // this sub-group's transpose tile
+    cplx *X = reinterpret_cast<cplx *>(base + kGlweWords * 8 + 3 * 8192);             // [3][512] spectra, slot-major
+    const int tbar = 1 + team * 4, sbar = 2 + team * 4 + sub;
+    const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+    uint16_t *rot = reinterpret_cast<uint16_t *>(ring + kLlRing * kBrTileBytes + 64) + team * kLweN;
+    for (int q = u; q < kLweN; q += kLlTeamThreads) rot[q] = (uint16_t)(modswitch_dev(a[q]) & 2047);
+    u64x2 *p = acc + sub * 512;  // the polynomial this sub-group owns
+    {
+        const int bt = modswitch_dev(a[kLweN]);
+        for (int jj = t; jj < 512; jj += 64) {
+            u64x2 b{0, 0};
+            if (sub == 2) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int j = jj + 512 * h;
+                    const int e = (j + bt) & 2047;
+                    const int i = e & 1023;
+                    uint64_t val = 1ull << (61 - 2 * (i & 7));
+                    const bool neg = (i < 512) != ((e & 1024) != 0);
+                    (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
+                }
+            }
+            p[jj] = b;
+        }
+    }
+    named_sync(tbar, kLlTeamThreads);
+    Twiddles tw;
+    load_twiddles_x(tw, twtab, t);
+
+#pragma unroll 1
+    for (int i = 0; i < kLweN; i++) {
+        const int d = rot[i];
+        if (producer && i >= 1) {
+#pragma unroll 1
+            for (int b = 0; b < kLlRing; b++) {
+                mbar_wait(empty + b, (i - 1) & 1);
+                tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)(i * 3 + b) * kBrTileBytes, kBrTileBytes, full + b);
+            }
+        }
+        __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
+        if (d == 0) {  // trivial rotation: the product is exactly zero, only the ring bookkeeping remains
+#pragma unroll 1
+            for (int b = 0; b < kLlRing; b++) {
+                mbar_wait(full + b, i & 1);
+                mbar_arrive(empty + b);
+            }
+            continue;
+        }
+        cplx v[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int jj = t + 64 * m;
+            const int e0 = (jj - d) & 2047;
+            const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];
+            const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
+            const bool sw = (e0 & 512) != 0;
+            const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
+            const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
+            const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
+            const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
+            v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
+                        digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
+        }
+        fwd_p1(v, scr, tw, t);
+        named_sync(sbar, 64);
+        fwd_p2x(v, scr, tw, t);
+        exchange8<-1>(v, t & 7);
+        fwd_p3x(v);
+        named_sync(tbar, kLlTeamThreads);  // every sub-group has finished reading the previous step's spectra
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++) X[sub * 512 + k3 * 64 + t] = v[k3];
+        named_sync(tbar, kLlTeamThreads);
+        cplx out[8];
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++) out[k3] = cplx{0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            mbar_wait(full + r, i & 1);
+            const cplx *key = reinterpret_cast<const cplx *>(ring + r * kBrTileBytes) + sub * 512 + t;
+            const cplx *S = X + r * 512 + t;
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) cfma(out[k3], S[k3 * 64], key[k3 * 64]);
+            mbar_arrive(empty + r);
+        }
+        inv_p3x(out);
+        exchange8<1>(out, t & 7);
+        inv_p2x(out, scr, tw, t);
+        named_sync(sbar, 64);
+        inv_p1(out, scr, tw, t);
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            u64x2 w = p[t + 64 * m];
+            w.lo += torus_from_scaled(out[m].x);
+            w.hi += torus_from_scaled(out[m].y);
+            p[t + 64 * m] = w;
+        }
+        named_sync(sbar, 64);  // polynomial `sub` is complete before the next build's rotated reads
+    }
+    uint64_t *o = acc_out + (size_t)ct * kGlweWords + sub * 1024;
+    for (int w = t; w < 512; w += 64) {
+        const u64x2 x = p[w];
+        o[w] = x.lo;
+        o[w + 512] = x.hi;
+    }
+}
+
 static int br_variant()
 {
     static int v = -1;
@@ -794,6 +951,7 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     bool &attr = attr_done[attr_dev & 63];
     if (!attr) {
         cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, kLlSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
@@ -801,6 +959,18 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         attr = true;
     }
     const int grid = (count + kBrGroups - 1) / kBrGroups;
+    static int ll_sms[64] = {0};
+    if (!ll_sms[attr_dev & 63]) cudaDeviceGetAttribute(&ll_sms[attr_dev & 63], cudaDevAttrMultiProcessorCount, attr_dev);
+    // small batches (at most kLlTeams ciphertexts per SM): the 192-thread-team kernel, 2.4x shorter per blind rotation
+    static int ll_mode = -1;  // CBS_BR_LOWLAT: 0 = never, 1 = auto (default), 2 = always
+    if (ll_mode < 0) {
+        const char *e = getenv("CBS_BR_LOWLAT");
+        ll_mode = e ? atoi(e) : 1;
+    }
+    if (br_variant() >= 3 && (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * ll_sms[attr_dev & 63]))) {
+        k_blind_rotate_ll<<<(count + kLlTeams - 1) / kLlTeams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+        return;
+    }
     if (br_variant() == 0)
         k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
     else {

@@ -69,6 +69,32 @@ def test_blind_rotate_matches_oracle(ctx, orc, orc_keys, keyset):
             assert abs(err) < 2 ** 52, (i, lvl, np.log2(abs(err) + 1))
 
 
+def test_blind_rotate_throughput_and_team_kernels(ctx, orc, orc_keys, keyset):
+    """Batches of at most 2 ciphertexts per SM run the 192-thread-team kernel (the tests above), larger ones the
+    4-groups-per-CTA throughput kernel: a 300-ciphertext batch must decrypt correctly, match the oracle in its single-step
+    arithmetic, and agree in phase with the team kernel on the same inputs."""
+    bits = _bits(300, 31)
+    small = keyset.encrypt_bits_small(bits, 33)
+    big = ctx.blind_rotate(small)            # throughput kernel
+    team = ctx.blind_rotate(small[:6])       # team kernel
+    ph = glwe_phase(big, keyset.glwe_sk)
+    for lvl in range(7):
+        val = (ph[:, lvl] + np.uint64(1 << (63 - 2 * (lvl + 1))))
+        want = bits.astype(np.uint64) << np.uint64(64 - 2 * (lvl + 1))
+        assert log2max(sdiff(val, want)) < 52
+    d = sdiff(ph[:6], glwe_phase(team, keyset.glwe_sk))
+    assert log2max(d) < 52.0, log2max(d)
+    # single external product through the throughput kernel: ciphertext-level agreement with the oracle
+    rng = np.random.default_rng(22)
+    lwe = np.zeros((300, 769), dtype=np.uint64)
+    for i in range(300):
+        lwe[i, (37 * i + 5) % 768] = rng.integers(1 << 56, 1 << 63, dtype=np.uint64)
+        lwe[i, 768] = rng.integers(0, 1 << 63, dtype=np.uint64)
+    got = ctx.blind_rotate(lwe)
+    want = orc.blind_rotate(orc_keys, lwe[:4])
+    assert log2max(sdiff(got[:4], want)) < 44
+
+
 def test_glev_from_acc_bit_exact(ctx, orc):
     acc = np.random.default_rng(3).integers(0, 2 ** 64, (5, 3072), dtype=np.uint64)
     got = ctx.glev_from_acc(acc)
