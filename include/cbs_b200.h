@@ -191,6 +191,9 @@ int cbs_max_plan_check(const uint16_t *vals, int nvals, uint16_t *result, int64_
  * -> out[16] big LWE (MSB first).  nvals must be even.  Boolean circuit of nibble-product, population-count
  * and nibble-adder LUT ladders over circuit-bootstrapped bits (csrc/host/ip_plan.h). */
 int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out);
+/* sum of nvals 16-bit values mod 2^16 (the compression stage of the inner product alone; same formats): combines the
+ * per-GPU partial inner products when the pairs are sharded across GPUs */
+int cbs_sum_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out);
 /* Host-only dry run of the SAME circuit plan on cleartext values (no GPU, no ciphertexts): checks the circuit
  * against the harness formula in the CPU test suite and reports its size.  Any output pointer may be NULL. */
 int cbs_inner_product_plan_check(const uint16_t *vals, int nvals, uint16_t *result, int64_t *circuit_bootstraps,

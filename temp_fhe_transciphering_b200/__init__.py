@@ -413,6 +413,14 @@ class Context:
         _check(lib().cbs_max_u16_lut(self._h, pi, nvals, po), "cbs_max_u16_lut")
         return out
 
+    def sum_u16(self, lwe_bits):
+        """sum of the values mod 2^16 (combines per-GPU partial inner products); same formats as max_u16."""
+        a, pi = _u64(np.reshape(lwe_bits, (-1, LWE_BIG)))
+        nvals = a.shape[0] // 16
+        out, po = _out((16, LWE_BIG))
+        _check(lib().cbs_sum_u16(self._h, pi, nvals, po), "cbs_sum_u16")
+        return out
+
     def inner_product_u16(self, lwe_bits):
         """mini-workload #2 (harness/cleartext_impl.py:65-70): [nvals*16][2049] -> [16][2049] encrypting
         sum_i (x_i * y_i mod 2^16) mod 2^16, x = first half of the values, y = second half."""

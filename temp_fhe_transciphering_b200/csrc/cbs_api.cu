@@ -1149,6 +1149,15 @@ int cbs_inner_product_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t 
     return run_lut_plan(ctx, cbs_host::ip_make_plan(nvals), in, out);
 }
 
+// Sum of nvals 16-bit values mod 2^16 (the column-compression stage of the inner product alone): combines per-GPU
+// partial inner products when the pairs are sharded across GPUs.
+int cbs_sum_u16(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
+{
+    ENTER(ctx);
+    if (nvals <= 0 || !in || !out) return set_error("cbs_sum_u16: bad argument"), CBS_ERR_ARG;
+    return run_lut_plan(ctx, cbs_host::sum_make_plan(nvals), in, out);
+}
+
 // Maximum as a LUT circuit (host/ip_plan.h max_make_plan): noise independent of the data and of the tree depth.
 int cbs_max_u16_lut(cbs_ctx *ctx, const uint64_t *in, int nvals, uint64_t *out)
 {

@@ -82,47 +82,15 @@ struct IpPlan {
     }
 };
 
-inline IpPlan ip_make_plan(int nvals)
+// Column compression + final addition (phases A and B above): reduces `col` (col[c] = pool indices of the bits of
+// weight 2^c) to one bit per column, appending the layers to `plan`.
+inline void ip_compress_columns(IpPlan &plan, std::vector<std::vector<int>> &col, int &pool)
 {
-    IpPlan plan;
-    plan.nvals = nvals;
-    plan.nin_bits = nvals * 16;
-    const int P = nvals / 2;
-    int pool = nvals * 16;
-    std::vector<std::vector<int>> col(16);
     auto alloc4 = [&]() {
         int b = pool;
         pool += 4;
         return b;
     };
-    auto in_bit = [](int value, int weight) { return value * 16 + (15 - weight); };
-
-    // layer 0: nibble products
-    if (P > 0) {
-        IpLayer L;
-        L.cbs.resize((size_t)nvals * 16);
-        for (int i = 0; i < nvals * 16; i++) L.cbs[i] = i;  // position == pool index
-        for (int i = 0; i < P; i++)
-            for (int k = 0; k < 4; k++)
-                for (int l = 0; k + l < 4; l++) {
-                    IpJob j;
-                    for (int b = 0; b < 4; b++) {
-                        j.sel[b] = in_bit(i, 4 * k + b);
-                        j.sel[4 + b] = in_bit(P + i, 4 * l + b);
-                    }
-                    j.lut = kIpMul;
-                    for (int a = 0; a < 2; a++) {
-                        const int c0 = 4 * (k + l) + 4 * a;
-                        if (c0 >= 16) break;
-                        j.acc = a;
-                        j.out = alloc4();
-                        L.jobs.push_back(j);
-                        for (int q = 0; q < 4; q++) col[c0 + q].push_back(j.out + q);
-                    }
-                }
-        plan.layers.push_back(std::move(L));
-    }
-
     for (;;) {
         size_t maxh = 0;
         for (int c = 0; c < 16; c++) maxh = col[c].size() > maxh ? col[c].size() : maxh;
@@ -189,6 +157,60 @@ inline IpPlan ip_make_plan(int nvals)
     }
     for (int c = 0; c < 16; c++) plan.result[c] = col[c].empty() ? -1 : col[c][0];
     plan.pool_size = pool;
+}
+
+inline IpPlan ip_make_plan(int nvals)
+{
+    IpPlan plan;
+    plan.nvals = nvals;
+    plan.nin_bits = nvals * 16;
+    const int P = nvals / 2;
+    int pool = nvals * 16;
+    std::vector<std::vector<int>> col(16);
+    auto in_bit = [](int value, int weight) { return value * 16 + (15 - weight); };
+
+    // layer 0: nibble products
+    if (P > 0) {
+        IpLayer L;
+        L.cbs.resize((size_t)nvals * 16);
+        for (int i = 0; i < nvals * 16; i++) L.cbs[i] = i;  // position == pool index
+        for (int i = 0; i < P; i++)
+            for (int k = 0; k < 4; k++)
+                for (int l = 0; k + l < 4; l++) {
+                    IpJob j;
+                    for (int b = 0; b < 4; b++) {
+                        j.sel[b] = in_bit(i, 4 * k + b);
+                        j.sel[4 + b] = in_bit(P + i, 4 * l + b);
+                    }
+                    j.lut = kIpMul;
+                    for (int a = 0; a < 2; a++) {
+                        const int c0 = 4 * (k + l) + 4 * a;
+                        if (c0 >= 16) break;
+                        j.acc = a;
+                        j.out = pool;
+                        pool += 4;
+                        L.jobs.push_back(j);
+                        for (int q = 0; q < 4; q++) col[c0 + q].push_back(j.out + q);
+                    }
+                }
+        plan.layers.push_back(std::move(L));
+    }
+    ip_compress_columns(plan, col, pool);
+    return plan;
+}
+
+// Sum of nvals 16-bit values mod 2^16: the compression stage alone.  Combines the per-GPU partial inner products when
+// the pairs are sharded across GPUs (each GPU's partial sum is 16 bit ciphertexts).
+inline IpPlan sum_make_plan(int nvals)
+{
+    IpPlan plan;
+    plan.nvals = nvals;
+    plan.nin_bits = nvals * 16;
+    int pool = nvals * 16;
+    std::vector<std::vector<int>> col(16);
+    for (int v = 0; v < nvals; v++)
+        for (int w = 0; w < 16; w++) col[(size_t)w].push_back(v * 16 + (15 - w));
+    ip_compress_columns(plan, col, pool);
     return plan;
 }
 

@@ -1,4 +1,4 @@
-// server_encrypted_compute <size> — drop-in for the reference stage 8 executable
+// server_encrypted_compute <size> [workload] — drop-in for the reference stage 8 executable
 // (submission/src/bin/server_encrypted_compute.rs:99-359): reads
 // io/<s>/ciphertext_aes_download/result.bin (16 LWE bits per u16, MSB first), computes the
 // encrypted maximum and writes io/<s>/ciphertexts_download/result.bin (16 LWE).
@@ -6,7 +6,14 @@
 // The harness selects the mini-workload with --mini_workload but does not pass it on
 // (harness/run_submission.py:97,129-131); a second argument "1" or CBS_MINI_WORKLOAD=1 selects the inner
 // product mod 2^16 of the first half of the values with the second half instead of the maximum.
+// With several visible GPUs (CBS_GPUS limits the count) the values (max) or pairs (inner product) are sharded
+// contiguously, every GPU reduces its shard with replicated keys, and GPU 0 combines the 16-ciphertext partial
+// results (a max over them / their sum mod 2^16): SURVEY.md 8(e), no collective in the data path.
 #include "stage_common.h"
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
 
 int main(int argc, char **argv)
 {
@@ -20,18 +27,64 @@ int main(int argc, char **argv)
         fprintf(stderr, "Error: lwe_ciphertext_list length is not a multiple of 16\n");
         return 1;
     }
+    const int nvals = (int)(count / 16);
+    const char *mw = argc >= 3 ? argv[2] : getenv("CBS_MINI_WORKLOAD");
+    const bool inner = mw && atoi(mw) == 1;
+    if (inner && (nvals & 1)) {
+        fprintf(stderr, "Error: the inner product needs an even number of values\n");
+        return 1;
+    }
     cbs_keyset *ks = nullptr;
     STAGE_TRY(cbs_keyset_load_dir(io_dir.c_str(), 0, &ks));
-    cbs_ctx *ctx = nullptr;
-    STAGE_TRY(cbs_ctx_create(ks, 0, &ctx));
-    std::vector<uint64_t> out((size_t)16 * CBS_LWE_BIG_WORDS);
-    const char *mw = argc >= 3 ? argv[2] : getenv("CBS_MINI_WORKLOAD");
-    if (mw && atoi(mw) == 1)
-        STAGE_TRY(cbs_inner_product_u16(ctx, data, (int)(count / 16), out.data()));
-    else
-        STAGE_TRY(cbs_max_u16(ctx, data, (int)(count / 16), out.data()));
+    int ngpu = 0;
+    if (cbs_device_count(&ngpu) != CBS_OK || ngpu == 0) {
+        fprintf(stderr, "Error: no CUDA device (this executable has no CPU fallback)\n");
+        return 1;
+    }
+    if (const char *e = getenv("CBS_GPUS")) ngpu = std::max(1, std::min(ngpu, atoi(e)));
+    const int units = inner ? nvals / 2 : nvals;        // pairs or values
+    ngpu = std::max(1, std::min(ngpu, units / 8));      // a shard below 8 units is not worth a context
+    const size_t vw = (size_t)16 * CBS_LWE_BIG_WORDS;   // words per value
+    std::vector<uint64_t> out(vw);
+
+    if (ngpu == 1) {
+        cbs_ctx *ctx = nullptr;
+        STAGE_TRY(cbs_ctx_create(ks, 0, &ctx));
+        if (inner) STAGE_TRY(cbs_inner_product_u16(ctx, data, nvals, out.data()));
+        else STAGE_TRY(cbs_max_u16(ctx, data, nvals, out.data()));
+        cbs_ctx_destroy(ctx);
+    } else {
+        std::vector<uint64_t> partial((size_t)ngpu * vw);
+        std::vector<int> rc(ngpu, 0);
+        std::vector<std::string> err(ngpu);
+        std::vector<cbs_ctx *> ctxs(ngpu, nullptr);
+        std::vector<std::thread> workers;
+        for (int g = 0; g < ngpu; g++) {
+            workers.emplace_back([&, g]() {
+                const int u0 = (int)((long)units * g / ngpu), u1 = (int)((long)units * (g + 1) / ngpu);
+                rc[g] = cbs_ctx_create(ks, g, &ctxs[g]);
+                if (rc[g] == CBS_OK && !inner)
+                    rc[g] = cbs_max_u16(ctxs[g], data + (size_t)u0 * vw, u1 - u0, partial.data() + (size_t)g * vw);
+                if (rc[g] == CBS_OK && inner) {  // this shard's x values followed by its y values
+                    std::vector<uint64_t> in((size_t)2 * (u1 - u0) * vw);
+                    memcpy(in.data(), data + (size_t)u0 * vw, (size_t)(u1 - u0) * vw * 8);
+                    memcpy(in.data() + (size_t)(u1 - u0) * vw, data + (size_t)(units + u0) * vw, (size_t)(u1 - u0) * vw * 8);
+                    rc[g] = cbs_inner_product_u16(ctxs[g], in.data(), 2 * (u1 - u0), partial.data() + (size_t)g * vw);
+                }
+                if (rc[g] != CBS_OK) err[g] = cbs_last_error();
+            });
+        }
+        for (auto &w : workers) w.join();
+        for (int g = 0; g < ngpu; g++)
+            if (rc[g] != CBS_OK) {
+                fprintf(stderr, "Error: GPU %d: %s\n", g, err[g].c_str());
+                return 1;
+            }
+        if (inner) STAGE_TRY(cbs_sum_u16(ctxs[0], partial.data(), ngpu, out.data()));
+        else STAGE_TRY(cbs_max_u16(ctxs[0], partial.data(), ngpu, out.data()));
+        for (cbs_ctx *c : ctxs) cbs_ctx_destroy(c);
+    }
     STAGE_TRY(cbs_lwe_list_save((io_dir + "/ciphertexts_download/result.bin").c_str(), out.data(), 16, CBS_LWE_BIG_WORDS));
-    cbs_ctx_destroy(ctx);
     cbs_keyset_free(ks);
     cbs_free(data);
     return 0;

@@ -40,3 +40,22 @@ def gather_results(local, nblocks, rank, world, dist=None, device=None):
         return None
     parts = [outs[r][: sizes[r][1] - sizes[r][0]].cpu().numpy().view(np.uint64) for r in range(world)]
     return np.concatenate(parts, axis=0)
+
+
+def pair_range(npairs, rank, world):
+    """Contiguous [p0, p1) of the inner product's `npairs` (x_i, y_i) pairs owned by `rank`."""
+    return npairs * rank // world, npairs * (rank + 1) // world
+
+
+def shard_inner_product_values(lwe_bits, rank, world):
+    """Rows of [nvals*16][2049] bit ciphertexts this rank needs for its partial inner product: its slice of the
+    first half (x) followed by the same slice of the second half (y), i.e. again a (first half, second half) input."""
+    a = np.asarray(lwe_bits, dtype=np.uint64).reshape(-1, 16, 2049)
+    npairs = a.shape[0] // 2
+    p0, p1 = pair_range(npairs, rank, world)
+    return np.concatenate([a[p0:p1], a[npairs + p0:npairs + p1]], axis=0).reshape(-1, 2049)
+
+
+def value_range(nvals, rank, world):
+    """Contiguous [v0, v1) of the max workload's values owned by `rank`."""
+    return nvals * rank // world, nvals * (rank + 1) // world

@@ -212,6 +212,20 @@ def test_aes_transcipher_two_blocks(ctx, orc, orc_keys, keyset, aes_key, trans_k
     assert abs(std - ostd) < 0.5
 
 
+def test_aes_transcipher_medium_instance_size(ctx, keyset, aes_key, trans_key):
+    """BASELINE.json configs[2] at its full size on one GPU: 64 blocks = 8192 bit-ciphertexts per round (one chunk, two
+    lanes, throughput blind-rotation kernel).  Size-independent checks: bit-exact decryption of all 8192 output bits
+    against the cleartext and the output-noise tolerance of the reference (+0.3 bit)."""
+    import aes_clear
+    import ref_io
+    pt = bytes(np.random.default_rng(64).integers(0, 256, 16 * 64, dtype=np.uint8))
+    ct = aes_clear.ecb_encrypt(aes_key, pt)
+    got = ctx.aes_to_lwe_transciphering(ct, *trans_key)
+    bits, std, mx = ref_io.noise_stats(got.reshape(-1, 2049), keyset.glwe_sk)
+    assert np.packbits(bits).tobytes() == pt
+    assert std < 58.5 and mx < 61.5, (std, mx)
+
+
 def test_aes_ctr_transcipher(ctx, orc, orc_keys, keyset, aes_key):
     """CTR mode (harness sizes 1/2): forward AES of the public counters xor the ciphertext."""
     import aes_clear
@@ -271,3 +285,17 @@ def test_inner_product_u16(ctx, keyset):
         want = sum((x * y) % 65536 for x, y in zip(vals[: n // 2], vals[n // 2:])) % 65536
         assert ref_io.bits_to_u16(dec) == [want], (n, vals)
         assert mx < 61.5
+
+
+def test_sum_u16_and_sharded_inner_product(ctx, keyset):
+    """cbs_sum_u16 (the combine step of the multi-GPU inner product) and the shard -> partial -> sum route on one GPU."""
+    import ref_io
+    from temp_fhe_transciphering_b200 import sharding
+    vals = np.random.default_rng(77).integers(0, 65536, 20).tolist()
+    bits = np.array([(v >> (15 - i)) & 1 for v in vals for i in range(16)], dtype=np.uint8)
+    lwe = keyset.encrypt_bits_big(bits, 78)
+    dec = ref_io.decode_bit(ref_io.lwe_phase(ctx.sum_u16(lwe[:5 * 16]), keyset.glwe_sk))
+    assert ref_io.bits_to_u16(dec) == [sum(vals[:5]) % 65536]
+    parts = [ctx.inner_product_u16(sharding.shard_inner_product_values(lwe, r, 3)) for r in range(3)]
+    dec = ref_io.decode_bit(ref_io.lwe_phase(ctx.sum_u16(np.concatenate(parts)), keyset.glwe_sk))
+    assert ref_io.bits_to_u16(dec) == [sum((x * y) % 65536 for x, y in zip(vals[:10], vals[10:])) % 65536]
