@@ -541,6 +541,33 @@ __device__ __forceinline__ void inv_fft_s(cplx v[8], Group &g, const Twiddles &t
     group_sync(g.bar);
     inv_p1(v, s, tw, g.t);
 }
+// shuffle-exchange variant with the rotated pass-2 twiddles in shared memory (t2xs = table[r*8 + a] + (t & 7))
+__device__ __forceinline__ void fwd_p2x_s(cplx v[8], const cplx *scr, const cplx *t2xs, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) v[mp] = scr[slot(k1, tp, mp)];
+    dft8<false>(v);
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = cmul(v[r], t2xs[r * 8]);
+}
+__device__ __forceinline__ void inv_p2x_s(cplx v[8], cplx *scr, const cplx *t2xs, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = cmul_conj(v[r], t2xs[r * 8]);
+    dft8<true>(v);
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
+}
+__device__ __forceinline__ void fill_t2x_table(cplx *t2tab, const double *twtab, int tid)
+{
+    if (tid < 64) {
+        const int a = tid >> 3, r = tid & 7;
+        const double *x = twtab + kTwiddleXOffset;
+        t2tab[r * 8 + a] = cplx{x[(512 + a * 8 + r) * 2], x[(512 + a * 8 + r) * 2 + 1]};
+    }
+}
 // fill a 64-entry shared table with the pass-2 twiddles transposed to [k2][t'] (conflict-free reads)
 __device__ __forceinline__ void fill_t2_table(cplx *t2tab, const double *twtab, int tid)
 {
@@ -1232,8 +1259,10 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v2(const uint64_t *
 constexpr int kTr3UnitSmem = kGlweWords * 8 + 2 * 8192 + 2 * 8192;  // cur 24 KB + 2 tiles + exchange = 56 KB
 constexpr int kTr3SmemBytes = kTr2Glwe * kTr3UnitSmem + 4 * kBrTileBytes + 1024 + 64;
 
-// (Tried and rejected: the shuffle-exchange transforms of the blind rotation in this kernel - 5.3 ms instead of
-//  3.8 ms per 7168 GLWE at 255 registers with spills, so the trace keeps the shared-memory transposes.)
+// XCH: shuffle-exchange transforms (fft512.cuh "x"): one shared-memory transpose and one sub-group barrier per
+// transform instead of two; both sub-groups produce spectra with the same per-lane phase, so the exchange tile and
+// the (plain-layout) key tiles are used unchanged.
+template <bool XCH>
 __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *__restrict__ in,
                                                                  uint64_t *__restrict__ out, int count, int from_acc,
                                                                  const double *__restrict__ auto_f,
@@ -1249,7 +1278,8 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + 4 * kBrTileBytes + 1024);
     uint64_t *empty = full + 4;
     const int active_units = min(kTr2Glwe, count - blockIdx.x * kTr2Glwe);
-    fill_t2_table(t2tab, twtab, threadIdx.x);
+    if (XCH) fill_t2x_table(t2tab, twtab, threadIdx.x);
+    else fill_t2_table(t2tab, twtab, threadIdx.x);
     if (threadIdx.x == 0) {
         for (int b = 0; b < 4; b++) {
             mbar_init(full + b, 1);
@@ -1286,7 +1316,8 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     const int sbar = 1 + gl * 2 + sub;
     const int ubar = 5 + gl;
     Twiddles tw;
-    load_twiddles(tw, twtab, t);
+    if (XCH) load_twiddles_x(tw, twtab, t);
+    else load_twiddles(tw, twtab, t);
     {
         const int u = threadIdx.x & 127;
         if (from_acc) {
@@ -1356,9 +1387,15 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
                 want = -1;
             }
             __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-            fwd_p2_s(v, scr, t2s, t);
-            group_sync(sbar);
-            fwd_p3(v, scr, t);
+            if (XCH) {
+                fwd_p2x_s(v, scr, t2s, t);
+                exchange8<-1>(v, t & 7);
+                fwd_p3x(v);
+            } else {
+                fwd_p2_s(v, scr, t2s, t);
+                group_sync(sbar);
+                fwd_p3(v, scr, t);
+            }
             cplx *Xw = X + sub * 512 + t;
             const cplx *Xr = X + (1 - sub) * 512 + t;
 #pragma unroll
@@ -1392,14 +1429,25 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
         const int shift = sub ? 41 : 0;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            inv_p3(acc[c], scr, t);
-            group_sync(sbar);
-            if (producer && want >= 0) {
-                produce(want);
-                want = -1;
+            if (XCH) {
+                inv_p3x(acc[c]);
+                exchange8<1>(acc[c], t & 7);
+                if (producer && want >= 0) {
+                    produce(want);
+                    want = -1;
+                }
+                __syncwarp();
+                inv_p2x_s(acc[c], scr, t2s, t);
+            } else {
+                inv_p3(acc[c], scr, t);
+                group_sync(sbar);
+                if (producer && want >= 0) {
+                    produce(want);
+                    want = -1;
+                }
+                __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
+                inv_p2_s(acc[c], scr, t2s, t);
             }
-            __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-            inv_p2_s(acc[c], scr, t2s, t);
             group_sync(sbar);
             inv_p1(acc[c], scr, tw, t);
             u64x2 *p = cur + c * 512;
@@ -1452,17 +1500,21 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
         }
         cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
         cudaFuncSetAttribute(k_trace_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr2SmemBytes);
-        cudaFuncSetAttribute(k_trace_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
+        cudaFuncSetAttribute(k_trace_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
+        cudaFuncSetAttribute(k_trace_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
         init = true;
     }
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("CBS_TRACE_VARIANT");
-        variant = e ? atoi(e) : 3;
+        variant = e ? atoi(e) : 4;  // 2 = LDG keys, 3 = TMA ring, 4 = TMA ring + shuffle-exchange transforms
     }
-    if (variant == 3)
-        k_trace_v3<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
-                                                                                               K.auto_f, K.tw);
+    if (variant >= 4)
+        k_trace_v3<true><<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
+                                                                                                     K.auto_f, K.tw);
+    else if (variant == 3)
+        k_trace_v3<false><<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
+                                                                                                      K.auto_f, K.tw);
     else
         k_trace_v2<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr2SmemBytes, s>>>(in, out, count, from_acc,
                                                                                                K.auto_f, K.tw);

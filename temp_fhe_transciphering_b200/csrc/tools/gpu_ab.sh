@@ -1,4 +1,5 @@
-# development helper: run under gpurun from the repo root; writes logs to gpurun_out/
 set -x
-mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+for tv in 3 4; do
+  CBS_TRACE_VARIANT=$tv timeout -s KILL 120 python temp_fhe_transciphering_b200/csrc/tools/brbench.py 1024
+  CBS_TRACE_VARIANT=$tv timeout -s KILL 200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "trace or circuit_bootstrap or two_blocks" 2>&1 | tail -2
+done
