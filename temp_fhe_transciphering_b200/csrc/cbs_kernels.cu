@@ -931,8 +931,13 @@ __global__ void __launch_bounds__(kLlTeamThreads * kLlTeams, 1) k_blind_rotate_l
             mbar_wait(full + r, i & 1);
             const cplx *key = reinterpret_cast<const cplx *>(ring + r * kBrTileBytes) + sub * 512 + t;
             const cplx *S = X + r * 512 + t;
+            if (r == sub) {  // own spectrum: still in registers (sub-group uniform branch; 3.33 -> 3.17 ms)
 #pragma unroll
-            for (int k3 = 0; k3 < 8; k3++) cfma(out[k3], S[k3 * 64], key[k3 * 64]);
+                for (int k3 = 0; k3 < 8; k3++) cfma(out[k3], v[k3], key[k3 * 64]);
+            } else {
+#pragma unroll
+                for (int k3 = 0; k3 < 8; k3++) cfma(out[k3], S[k3 * 64], key[k3 * 64]);
+            }
             mbar_arrive(empty + r);
         }
         inv_p3x(out);
