@@ -823,17 +823,19 @@ __device__ __forceinline__ void named_sync(int bar, int nthreads)
 __global__ void __launch_bounds__(kLlTeamThreads * kLlTeams, 1) k_blind_rotate_ll(const uint64_t *__restrict__ lwe,
                                                                                     uint64_t *__restrict__ acc_out, int count,
                                                                                     const double *__restrict__ bsk_f,
-                                                                                    const double *__restrict__ twtab)
+                                                                                    const double *__restrict__ twtab, int teams)
 {
+    // `teams` (1 or 2) ciphertexts per CTA: up to one ciphertext per SM the second team stays idle and a blind
+    // rotation takes 2.3 ms instead of 3.2 ms (the two teams of a CTA share the shared-memory pipe)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int team = threadIdx.x / kLlTeamThreads;
     const int u = threadIdx.x - team * kLlTeamThreads;
     const int sub = u >> 6, t = u & 63;
-    const int ct = blockIdx.x * kLlTeams + team;
+    const int ct = (team < teams) ? blockIdx.x * teams + team : count;
     unsigned char *ring = smem_raw + (size_t)kLlTeams * kLlTeamSmem;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + kLlRing * kBrTileBytes);
     uint64_t *empty = full + kLlRing;
-    const int active_teams = min(kLlTeams, count - blockIdx.x * kLlTeams);
+    const int active_teams = min(teams, count - blockIdx.x * teams);
     if (threadIdx.x == 0) {
         for (int b = 0; b < kLlRing; b++) {
             mbar_init(full + b, 1);
@@ -1000,7 +1002,8 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         ll_mode = e ? atoi(e) : 1;
     }
     if (br_variant() >= 3 && (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * ll_sms[attr_dev & 63]))) {
-        k_blind_rotate_ll<<<(count + kLlTeams - 1) / kLlTeams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+        const int teams = count <= ll_sms[attr_dev & 63] ? 1 : kLlTeams;
+        k_blind_rotate_ll<<<(count + teams - 1) / teams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, teams);
         return;
     }
     if (br_variant() == 0)
