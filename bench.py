@@ -398,7 +398,7 @@ def main_ours(args):
             "launch_ms": br_ms, "ciphertexts_per_launch": B, "launches_per_step": 9 * lanes,
             "share_of_step": br_ms * 9 * lanes / (ms_total / args.steps),
             "share_note": "lanes overlap on the device, so kernel shares of the step sum to more than 1; "
-                          "ncu's serialised launch list (profiles/r01b_launch_summary.csv) gives 70.9 %",
+                          "ncu's serialised launch list (profiles/r01b_launch_summary.csv) gives 71.5 %",
             "hbm": {"bound": "hbm", "achieved": br_bytes / (br_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": br_bytes / (br_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src + " MEASURED_PEAKS.json",
                     "algorithmic_bytes_per_launch": br_bytes},
