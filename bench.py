@@ -50,6 +50,19 @@ def read_ncu_traffic():
         return None
 
 
+def read_ncu_metric(name):
+    """One metric of the throughput blind-rotation kernel from the committed ncu --set full summary (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01b_blind_rotate_ncu_full.csv")
+    try:
+        for line in open(p):
+            f = line.strip().split(",")
+            if f[0] == name:
+                return float(f[2])
+    except Exception:
+        pass
+    return None
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -395,6 +408,12 @@ def main_ours(args):
             "kernel": "k_blind_rotate", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved / fp64_peak, "traffic": read_ncu_traffic(),
             "traffic_source": "profiles/r01b_blind_rotate_ncu_full.csv (ncu --set full, same kernel, 1024 ciphertexts)", "peak_source": "FP64 FMA probe kernel, same run",
+            # why frac cannot reach 1: the FMA probe counts 2 flop per issue slot, the transform mixes DADD/DMUL (1 flop)
+            # with DFMA (2): 148.6 MFLOP per blind rotation are ~98.3 M FP64 instructions, so a saturated FP64 pipe would
+            # read frac = 0.755; ncu's pipe-active figure of the same kernel (profiles/) is the like-for-like utilisation
+            "frac_at_saturated_fp64_pipe": 148.6e6 / (768 * 64 * 2000.0 * 2.0),
+            "ncu_fp64_pipe_active_pct_of_elapsed": read_ncu_metric("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+            "ncu_shared_pipe_pct_of_peak": read_ncu_metric("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
             "launch_ms": br_ms, "ciphertexts_per_launch": B, "launches_per_step": 9 * lanes,
             "share_of_step": br_ms * 9 * lanes / (ms_total / args.steps),
             "share_note": "lanes overlap on the device, so kernel shares of the step sum to more than 1; "
