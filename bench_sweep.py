@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """bench_sweep.py — BASELINE.json configs[3] and [4]: batched circuit-bootstrap microbenchmark sweep
 (batch 1 .. 16384 LWE ciphertexts per launch, 1 GPU per process) and the full-round AES-128 run on
-many blocks.  Prints one JSON line per point; `--out` also writes them to a file.
+many blocks.  Prints one JSON line per point; `--out` also writes them to a file.  Under torchrun
+(`python -m torch.distributed.run --nproc-per-node N bench_sweep.py`) the batch / the blocks are sharded across the N ranks
+with replicated keys and no collective in the data path (strong scaling: `batch` and `blocks` are job totals); times are
+CUDA-event times, max over ranks, and rank 0 prints.
 
   python bench_sweep.py                      # CBS sweep 1..16384 + AES 64/256/1024 blocks
   python bench_sweep.py --cbs-only / --aes-only
@@ -35,8 +38,36 @@ def main():
     import ref_io
     import temp_fhe_transciphering_b200 as cbs
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(ok):
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
     ks = cbs.KeySet.generate(20261018)
-    ctx = cbs.Context(ks, 0)
+    ctx = cbs.Context(ks, local)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -44,35 +75,37 @@ def main():
     lines = []
 
     def emit(d):
-        print(json.dumps(d), flush=True)
-        lines.append(d)
+        if rank == 0:
+            print(json.dumps(d), flush=True)
+            lines.append(d)
 
     def timed(fn, reps):
         for _ in range(3):
             fn()
-        torch.cuda.synchronize()
+        sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(reps):
             fn()
         e1.record(stream)
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
+        sync_all()
+        return max_over_ranks(e0.elapsed_time(e1) / reps)
 
     if not args.aes_only:
         rng = np.random.default_rng(0)
-        B = 1
+        B = world  # job batch; every rank gets a contiguous share
         while B <= args.max_batch:
-            bits = rng.integers(0, 2, B, dtype=np.uint8)
+            mine = B * (rank + 1) // world - B * rank // world
+            bits = rng.integers(0, 2, max(mine, 1), dtype=np.uint8)
             small = torch.from_numpy(ks.encrypt_bits_small(bits, 100 + B).view(np.int64)).cuda()
-            acc = torch.empty((B, 3072), dtype=torch.int64, device="cuda")
-            ms_cbs = timed(lambda: ctx.circuit_bootstrap_dev(small.data_ptr(), B), 5 if B >= 64 else 20)
-            ms_br = timed(lambda: ctx.blind_rotate_dev(small.data_ptr(), acc.data_ptr(), B), 5 if B >= 64 else 20)
+            acc = torch.empty((max(mine, 1), 3072), dtype=torch.int64, device="cuda")
+            ms_cbs = timed(lambda: ctx.circuit_bootstrap_dev(small.data_ptr(), mine), 5 if B >= 64 else 20)
+            ms_br = timed(lambda: ctx.blind_rotate_dev(small.data_ptr(), acc.data_ptr(), mine), 5 if B >= 64 else 20)
             emit({"bench": "circuit_bootstrap_sweep", "batch": B, "ms_per_launch": ms_cbs, "cbs_per_s": B / (ms_cbs * 1e-3),
                   "blind_rotate_ms": ms_br, "blind_rotations_per_s": B / (ms_br * 1e-3),
                   "blind_rotate_fp64_tflops": 148.6e6 * B / (ms_br * 1e-3) * 1e-12,
-                  "blind_rotate_fp64_frac": 148.6e6 * B / (ms_br * 1e-3) * 1e-12 / fp64_peak,
-                  "bsk_stream_gbs": (56_623_104 + B * 30_728) / (ms_br * 1e-3) * 1e-9, "n_gpus": 1})
+                  "blind_rotate_fp64_frac": 148.6e6 * B / (ms_br * 1e-3) * 1e-12 / (fp64_peak * world),
+                  "bsk_stream_gbs": world * (56_623_104 + mine * 30_728) / (ms_br * 1e-3) * 1e-9, "n_gpus": world})
             B *= 2
 
     if not args.cbs_only:
@@ -80,28 +113,32 @@ def main():
         tk = ks.gen_transciphering_keys(aes_key, 31337)
         ctx.upload_trans_key(*tk)
         for nb in args.aes_blocks:
+            if nb < world:
+                continue
             rng = np.random.default_rng(nb)
             pt = bytes(rng.integers(0, 256, 16 * nb, dtype=np.uint8))
             ct = aes_clear.ecb_encrypt(aes_key, pt)
-            d_ct = torch.frombuffer(bytearray(ct), dtype=torch.uint8).cuda()
-            d_out = torch.empty((nb, 128, 2049), dtype=torch.int64, device="cuda")
-            ctx.transcipher_dev(d_ct.data_ptr(), nb, d_out.data_ptr())  # warm-up (allocates workspaces)
-            torch.cuda.synchronize()
+            b0, b1 = nb * rank // world, nb * (rank + 1) // world  # this rank's contiguous blocks (sharding.block_range)
+            mine = b1 - b0
+            d_ct = torch.frombuffer(bytearray(ct[16 * b0:16 * b1]), dtype=torch.uint8).cuda()
+            d_out = torch.empty((mine, 128, 2049), dtype=torch.int64, device="cuda")
+            ctx.transcipher_dev(d_ct.data_ptr(), mine, d_out.data_ptr())  # warm-up (allocates workspaces)
+            sync_all()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 3 if nb <= 64 else 1
             e0.record(stream)
             for _ in range(reps):
-                ctx.transcipher_dev(d_ct.data_ptr(), nb, d_out.data_ptr())
+                ctx.transcipher_dev(d_ct.data_ptr(), mine, d_out.data_ptr())
             e1.record(stream)
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / reps
+            sync_all()
+            ms = max_over_ranks(e0.elapsed_time(e1) / reps)
             out = d_out.cpu().numpy().view(np.uint64).reshape(-1, 2049)
             bits, std, mx = ref_io.noise_stats(out, ks.glwe_sk)
-            ok = np.packbits(bits).tobytes() == pt
+            ok = all_true(np.packbits(bits).tobytes() == pt[16 * b0:16 * b1])
             emit({"bench": "aes128_transcipher", "blocks": nb, "ms": ms, "blocks_per_s": nb / (ms * 1e-3),
                   "cbs_per_s": nb * 1152 / (ms * 1e-3), "verified": bool(ok), "noise_log2_std": std, "noise_log2_max": mx,
-                  "n_gpus": 1})
-    if not args.cbs_only and not args.aes_only or args.mini:
+                  "n_gpus": world})
+    if (not args.cbs_only and not args.aes_only or args.mini) and rank == 0:
         # mini-workloads of the three harness instances (workload_specification.md:8-9): max and inner product mod 2^16
         # over 8 / 64 / 512 u16 values given as bit ciphertexts; host buffers through the C ABI, second (warm) call timed
         for nvals in (8, 64, 512):
@@ -121,11 +158,14 @@ def main():
                 if name == "inner_product_u16":
                     _, d["circuit_bootstraps"], d["layers"], d["lut_ladders"] = cbs.inner_product_plan_check(np.array(vals, dtype=np.uint16))
                 emit(d)
-    if args.out:
+    if args.out and rank == 0:
         with open(args.out, "w") as f:
             for d in lines:
                 f.write(json.dumps(d) + "\n")
     ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -1001,10 +1001,23 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         const char *e = getenv("CBS_BR_LOWLAT");
         ll_mode = e ? atoi(e) : 1;
     }
+    auto launch_team = [&](const uint64_t *in, uint64_t *out, int n) {
+        const int teams = n <= ll_sms[attr_dev & 63] ? 1 : kLlTeams;
+        k_blind_rotate_ll<<<(n + teams - 1) / teams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(in, out, n, K.bsk_f, K.tw, teams);
+    };
     if (br_variant() >= 3 && (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * ll_sms[attr_dev & 63]))) {
-        const int teams = count <= ll_sms[attr_dev & 63] ? 1 : kLlTeams;
-        k_blind_rotate_ll<<<(count + teams - 1) / teams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, teams);
+        launch_team(lwe, acc, count);
         return;
+    }
+    // a last partial wave of at most two ciphertexts per SM also goes to the team kernel (3.2 / 2.4 ms instead of 5.8 ms)
+    if (br_variant() >= 3 && ll_mode == 1) {
+        const int wave = ll_sms[attr_dev & 63] * kBrGroups, rem = count % wave;
+        if (count > wave && rem > 0 && rem <= kLlTeams * ll_sms[attr_dev & 63]) {
+            const int head = count - rem;
+            k_blind_rotate_v3<false, true><<<head / kBrGroups, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw, kBrGroups, 0, nullptr);
+            launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, rem);
+            return;
+        }
     }
     if (br_variant() == 0)
         k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);

@@ -84,6 +84,12 @@ def test_blind_rotate_throughput_and_team_kernels(ctx, orc, orc_keys, keyset):
         assert log2max(sdiff(val, want)) < 52
     d = sdiff(ph[:6], glwe_phase(team, keyset.glwe_sk))
     assert log2max(d) < 52.0, log2max(d)
+    # one full wave through the throughput kernel + the remainder through the team kernel (mixed launch)
+    nsm = __import__("torch").cuda.get_device_properties(0).multi_processor_count
+    bits2 = _bits(4 * nsm + 5, 35)
+    ph2 = glwe_phase(ctx.blind_rotate(keyset.encrypt_bits_small(bits2, 36)), keyset.glwe_sk)
+    val = ph2[:, 0] + np.uint64(1 << 61)
+    assert log2max(sdiff(val, bits2.astype(np.uint64) << np.uint64(62))) < 52
     # single external product through the throughput kernel: ciphertext-level agreement with the oracle
     rng = np.random.default_rng(22)
     lwe = np.zeros((300, 769), dtype=np.uint64)
