@@ -45,6 +45,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the JSON lines
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def sync_all():
