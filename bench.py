@@ -250,8 +250,9 @@ def main_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's version banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # keep stdout to the one JSON line: this image exports NCCL_DEBUG=VERSION, whose banner goes to stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

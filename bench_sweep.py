@@ -45,7 +45,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the JSON lines
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # its banner goes to stdout; keep that to the JSON lines
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def sync_all():
