@@ -80,6 +80,13 @@ def test_small_instance_ctr_mode(tmp_path):
     got_max = [int(x) for x in (d / "io" / "small" / "result.txt").read_text().split()]
     assert got == vals
     assert got_max == [max(vals)]
+    # the other mini-workload on the same transciphered values (second argument = harness --mini_workload 1): 32 pairs, sharded
+    # over the visible GPUs when there are several, combined with cbs_sum_u16
+    run(os.path.join(BIN, "server_encrypted_compute"), "1")
+    run(os.path.join(REF, "client_decrypt_decode"))
+    run(os.path.join(REF, "client_postprocess"))
+    want = sum((x * y) % 65536 for x, y in zip(vals[:32], vals[32:])) % 65536
+    assert [int(x) for x in (d / "io" / "small" / "result.txt").read_text().split()] == [want]
 
 
 def test_all_ten_stages_ours(tmp_path):
