@@ -435,6 +435,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity)
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, int parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
@@ -1317,15 +1326,28 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
         const int s = n / 3, lev = 2 - (n % 3);
         return key_bytes + (size_t)((((s * 2 + i) * 2 + sp) * 3 + lev) * 3) * kFourierPolyDoubles * 8;
     };
-    auto produce = [&](int n) {
+    // refill of the four ring lanes for use n: `early` only takes the lanes every consumer has already released
+    // (non-blocking test right after a level's products), the regular call one barrier into the next transform
+    // blocks for the rest.  issued = bit mask of the lanes already requested for the pending use.
+    int issued = 0;
+    auto produce = [&](int n, bool early) {
         if (n >= 30) return;
 #pragma unroll
         for (int L = 0; L < 4; L++) {
-            if (n > 0) mbar_wait(empty + L, (n - 1) & 1);
+            if (issued & (1 << L)) continue;
+            if (n > 0) {
+                if (early) {
+                    if (!mbar_test(empty + L, (n - 1) & 1)) continue;
+                } else {
+                    mbar_wait(empty + L, (n - 1) & 1);
+                }
+            }
             tma_load_tile(ring + L * kBrTileBytes, tile_src(n, L & 1, L >> 1), kBrTileBytes, full + L);
+            issued |= 1 << L;
         }
+        if (!early) issued = 0;
     };
-    if (producer) produce(0);
+    if (producer) produce(0, false);
     __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
     int want = -1;  // next ring refill the producer owes (issued one barrier into the following transform)
 
@@ -1404,7 +1426,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
             fwd_p1(v, scr, tw, t);
             group_sync(sbar);
             if (producer && want >= 0) {
-                produce(want);
+                produce(want, false);
                 want = -1;
             }
             __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
@@ -1446,6 +1468,8 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
             mbar_arrive(empty + Loth);
             want = n + 1;
             unit_sync(ubar);  // partner finished reading the exchange tile before it is rewritten
+            if (producer) produce(want, true);  // lanes both units have released are refilled right away
+            __syncwarp();
         }
         const int shift = sub ? 41 : 0;
 #pragma unroll
@@ -1454,7 +1478,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
                 inv_p3x(acc[c]);
                 exchange8<1>(acc[c], t & 7);
                 if (producer && want >= 0) {
-                    produce(want);
+                    produce(want, false);
                     want = -1;
                 }
                 __syncwarp();
@@ -1463,7 +1487,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
                 inv_p3(acc[c], scr, t);
                 group_sync(sbar);
                 if (producer && want >= 0) {
-                    produce(want);
+                    produce(want, false);
                     want = -1;
                 }
                 __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
