@@ -973,6 +973,328 @@ __global__ void __launch_bounds__(kLlTeamThreads * kLlTeams, 1) k_blind_rotate_l
     }
 }
 
+// ---- v5: twiddles in tensor memory, 5 or 6 groups per SM ------------------------------------------------------
+// ncu r01b (profiles/r01b_blind_rotate_ncu_full.csv): v3 is a latency chain at 8 warps per SM (FP64 pipe 46 %, shared
+// pipe 58 %, issue slots 52 % of peak: three co-limiting pipes, none saturated), pinned there by 246 registers per
+// thread, 64 of which hold the per-thread pass-1/pass-2 twiddles.  Blackwell's tensor memory (256 KB per SM, idle in an
+// FP64 kernel) is addressable per lane with tcgen05.ld/st (SASS LDTM/STTM), so it serves as a second, thread-private
+// register file: every thread parks its 16 complex twiddles (64 words) there once and fetches them 4 at a time right
+// before the multiply.  With the key prefetch double buffer gone too, a group fits the 168-register cap of a 384-thread
+// CTA, and with ONE transpose tile per group (a second named barrier orders its reuse) and a ring of single-polynomial
+// key tiles, G = 6 groups (12 warps, 3 per scheduler) fit the 227 KB of shared memory.
+//   shared memory: G x (24 KB accumulator + 8 KB tile) + R x 8 KB ring + G x 1.5 KB rotations + barriers
+constexpr int kTwTmemWords = 64;  // per thread: t1x[8], t2x[8] as (re, im) doubles
+template <int G>
+struct Br5 {
+    static constexpr int kRing = (G >= 6) ? 3 : 6;            // key tiles of ONE Fourier polynomial (8 KB)
+    static constexpr int kPolyBytes = 512 * 16;
+    static constexpr int kGroupSmem = kGlweWords * 8 + kPolyBytes;  // 32 KB
+    static constexpr int kRingOff = G * kGroupSmem;
+    static constexpr int kBarOff = kRingOff + kRing * kPolyBytes;
+    static constexpr int kRotOff = kBarOff + 2 * kRing * 8 + 16;   // + tmem slot
+    static constexpr int kSmemBytes = kRotOff + G * kLweN * 2;
+};
+
+__device__ __forceinline__ void tmem_alloc_cols(uint32_t *slot, int cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cols(uint32_t addr, int cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// four complex doubles (16 words) of this thread's TMEM row, columns [col, col + 16)
+__device__ __forceinline__ void tmem_ld_c4_issue(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// the wait carries the destination registers as in/out operands so no use can be scheduled above it
+__device__ __forceinline__ void tmem_ld_c4_wait(uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+}
+__device__ __forceinline__ cplx tw_of(const uint32_t (&r)[16], int k)
+{
+    return cplx{__hiloint2double((int)r[4 * k + 1], (int)r[4 * k]), __hiloint2double((int)r[4 * k + 3], (int)r[4 * k + 2])};
+}
+__device__ __forceinline__ void tmem_st_c4(uint32_t taddr, const cplx *w)
+{
+    uint32_t r[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        r[4 * k] = (uint32_t)__double2loint(w[k].x);
+        r[4 * k + 1] = (uint32_t)__double2hiint(w[k].x);
+        r[4 * k + 2] = (uint32_t)__double2loint(w[k].y);
+        r[4 * k + 3] = (uint32_t)__double2hiint(w[k].y);
+    }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+// transform phases of fft512.cuh ("x" variant) with the per-thread twiddles fetched from TMEM: tm = this warp's TMEM
+// address (lane quarter + column base); columns [0, 32) = t1x[0..7], [32, 64) = t2x[0..7]
+__device__ __forceinline__ void fwd_p1_tm(cplx v[8], cplx *scr, uint32_t tm, int t)
+{
+    const double cr[8] = CBS_CM_RE, ci[8] = CBS_CM_IM;
+    uint32_t wa[16], wb[16];
+    tmem_ld_c4_issue(tm, wa);
+#pragma unroll
+    for (int m = 1; m < 8; m++) v[m] = cmul(v[m], cplx{cr[m], ci[m]});
+    dft8<false>(v);
+    const int a = t & 7, b = t >> 3;
+    tmem_ld_c4_wait(wa);
+    tmem_ld_c4_issue(tm + 16, wb);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) scr[slot(k1, a, b)] = cmul(v[k1], tw_of(wa, k1));
+    tmem_ld_c4_wait(wb);
+#pragma unroll
+    for (int k1 = 4; k1 < 8; k1++) scr[slot(k1, a, b)] = cmul(v[k1], tw_of(wb, k1 - 4));
+}
+__device__ __forceinline__ void fwd_p2x_tm(cplx v[8], const cplx *scr, uint32_t tm, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+    uint32_t wa[16], wb[16];
+    tmem_ld_c4_issue(tm + 32, wa);
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) v[mp] = scr[slot(k1, tp, mp)];
+    dft8<false>(v);
+    tmem_ld_c4_wait(wa);
+    tmem_ld_c4_issue(tm + 48, wb);
+#pragma unroll
+    for (int r = 0; r < 4; r++) v[r] = cmul(v[r], tw_of(wa, r));
+    tmem_ld_c4_wait(wb);
+#pragma unroll
+    for (int r = 4; r < 8; r++) v[r] = cmul(v[r], tw_of(wb, r - 4));
+}
+__device__ __forceinline__ void inv_p2x_tm(cplx v[8], cplx *scr, uint32_t tm, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+    uint32_t wa[16], wb[16];
+    tmem_ld_c4_issue(tm + 32, wa);
+    tmem_ld_c4_wait(wa);
+    tmem_ld_c4_issue(tm + 48, wb);
+#pragma unroll
+    for (int r = 0; r < 4; r++) v[r] = cmul_conj(v[r], tw_of(wa, r));
+    tmem_ld_c4_wait(wb);
+#pragma unroll
+    for (int r = 4; r < 8; r++) v[r] = cmul_conj(v[r], tw_of(wb, r - 4));
+    dft8<true>(v);
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
+}
+__device__ __forceinline__ void inv_p1_tm(cplx v[8], const cplx *scr, uint32_t tm, int t)
+{
+    const double cr[8] = CBS_CM_RE, ci[8] = CBS_CM_IM;
+    const int a = t & 7, b = t >> 3;
+    uint32_t wa[16], wb[16];
+    tmem_ld_c4_issue(tm, wa);
+    tmem_ld_c4_wait(wa);
+    tmem_ld_c4_issue(tm + 16, wb);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) v[k1] = cmul_conj(scr[slot(k1, a, b)], tw_of(wa, k1));
+    tmem_ld_c4_wait(wb);
+#pragma unroll
+    for (int k1 = 4; k1 < 8; k1++) v[k1] = cmul_conj(scr[slot(k1, a, b)], tw_of(wb, k1 - 4));
+    dft8<true>(v);
+#pragma unroll
+    for (int m = 1; m < 8; m++) v[m] = cmul_conj(v[m], cplx{cr[m], ci[m]});
+}
+
+template <int G>
+__global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v5(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out,
+                                                                int count, const double *__restrict__ bsk_f,
+                                                                const double *__restrict__ twtab)
+{
+    using L = Br5<G>;
+    constexpr int R = L::kRing;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6, warp = threadIdx.x >> 5;
+    const int ct = blockIdx.x * G + gi;
+    unsigned char *ring = smem_raw + L::kRingOff;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L::kBarOff);
+    uint64_t *empty = full + R;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + R);
+    const int active_groups = min(G, count - blockIdx.x * G);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < R; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, 64 * active_groups);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc_cols(tmem_slot, 256);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // warp w reaches TMEM lanes 32 * (w % 4) .. + 31 only; the (up to three) warps of a lane quarter take 64 columns each
+    const uint32_t tm = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(kTwTmemWords * (warp >> 2));
+    const int t = threadIdx.x & 63;
+    {
+        Twiddles tw;
+        load_twiddles_x(tw, twtab, t);
+        tmem_st_c4(tm, tw.t1);
+        tmem_st_c4(tm + 16, tw.t1 + 4);
+        tmem_st_c4(tm + 32, tw.t2);
+        tmem_st_c4(tm + 48, tw.t2 + 4);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    if (ct < count) {
+        const bool producer = (threadIdx.x == 0);
+        const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
+        constexpr int kTiles = kLweN * 9;
+        if (producer)
+            for (int b = 0; b < R; b++)
+                tma_load_tile(ring + b * L::kPolyBytes, bsk_bytes + (size_t)b * L::kPolyBytes, L::kPolyBytes, full + b);
+        __syncwarp();
+
+        unsigned char *base = smem_raw + (size_t)gi * L::kGroupSmem;
+        u64x2 *acc = reinterpret_cast<u64x2 *>(base);  // [3][512] pairs (coef j, coef j + 512)
+        cplx *scr = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+        const int bar_raw = 1 + gi, bar_war = 1 + G + gi;  // G <= 7: ids 1 .. 2G <= 14
+        const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+        uint16_t *rot = reinterpret_cast<uint16_t *>(smem_raw + L::kRotOff) + gi * kLweN;
+        for (int q = t; q < kLweN; q += 64) rot[q] = (uint16_t)(modswitch_dev(a[q]) & 2047);
+        {
+            const int bt = modswitch_dev(a[kLweN]);
+            for (int jj = t; jj < 512; jj += 64) {
+                acc[jj] = u64x2{0, 0};
+                acc[512 + jj] = u64x2{0, 0};
+                u64x2 b;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int j = jj + 512 * h;
+                    const int e = (j + bt) & 2047;
+                    const int i = e & 1023;
+                    uint64_t val = 1ull << (61 - 2 * (i & 7));
+                    const bool neg = (i < 512) != ((e & 1024) != 0);
+                    (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
+                }
+                acc[1024 + jj] = b;
+            }
+        }
+        group_sync(bar_raw);
+
+        int tile = 0;  // next key tile this thread consumes (same sequence in every thread)
+        // Producer (thread 0): tiles are requested in consumption order; tile q reuses the slot of tile q - R, so it can be
+        // requested once every group has released that one.  pump(0) takes whatever is free without blocking (called at
+        // several points of a row so that a request is never late); pump(n) blocks until tiles < n are requested (called
+        // right before this thread consumes them itself).  A dedicated producer warp would be the 13th warp of the
+        // CTA, and registers are allocated in units of 4 warps: it would cost every thread 40 registers.
+        int next_fill = R;
+        auto pump = [&](int need_upto) {
+            while (next_fill < kTiles) {
+                const int sl = next_fill % R, prev_use = next_fill / R - 1;
+                if (next_fill < need_upto) mbar_wait(empty + sl, prev_use & 1);
+                else if (!mbar_test(empty + sl, prev_use & 1)) break;
+                tma_load_tile(ring + sl * L::kPolyBytes, bsk_bytes + (size_t)next_fill * L::kPolyBytes, L::kPolyBytes, full + sl);
+                next_fill++;
+            }
+        };
+#pragma unroll 1
+        for (int i = 0; i < kLweN; i++) {
+            const int d = rot[i];
+            const bool skip = (d == 0);
+            cplx out[3][8];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+            for (int r = 0; r < 3; r++) {
+                if (producer) pump(0);
+                __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
+                if (!skip) {
+                    cplx v[8];
+                    const u64x2 *p = acc + r * 512;
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        const int jj = t + 64 * m;
+                        const int e0 = (jj - d) & 2047;
+                        const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];
+                        const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
+                        const bool sw = (e0 & 512) != 0;
+                        const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
+                        const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
+                        const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
+                        const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
+                        v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
+                                    digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
+                    }
+                    group_sync(bar_war);  // the partner warp has finished reading the tile of the previous transform
+                    fwd_p1_tm(v, scr, tm, t);
+                    group_sync(bar_raw);
+                    if (producer) pump(0);
+                    __syncwarp();
+                    fwd_p2x_tm(v, scr, tm, t);
+                    exchange8<-1>(v, t & 7);
+                    fwd_p3x(v);
+                    if (producer) pump(tile + 3);
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 3; c++, tile++) {
+                        const int buf = tile % R;
+                        mbar_wait(full + buf, (tile / R) & 1);
+                        const cplx *key = reinterpret_cast<const cplx *>(ring + buf * L::kPolyBytes) + t;
+#pragma unroll
+                        for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[k3 * 64]);
+                        mbar_arrive(empty + buf);
+                    }
+                } else {
+                    if (producer) pump(tile + 3);
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 3; c++, tile++) {
+                        const int buf = tile % R;
+                        mbar_wait(full + buf, (tile / R) & 1);
+                        mbar_arrive(empty + buf);
+                    }
+                }
+            }
+            if (skip) continue;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                inv_p3x(out[c]);
+                exchange8<1>(out[c], t & 7);
+                if (producer) pump(0);
+                __syncwarp();
+                group_sync(bar_war);
+                inv_p2x_tm(out[c], scr, tm, t);
+                group_sync(bar_raw);
+                inv_p1_tm(out[c], scr, tm, t);
+                u64x2 *p = acc + c * 512;
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    u64x2 w = p[t + 64 * m];
+                    w.lo += torus_from_scaled(out[c][m].x);
+                    w.hi += torus_from_scaled(out[c][m].y);
+                    p[t + 64 * m] = w;
+                }
+            }
+        }
+        group_sync(bar_raw);
+        uint64_t *o = acc_out + (size_t)ct * kGlweWords;
+        for (int w = t; w < 3 * 512; w += 64) {
+            const u64x2 x = acc[w];
+            const int c = w >> 9, jj = w & 511;
+            o[c * 1024 + jj] = x.lo;
+            o[c * 1024 + jj + 512] = x.hi;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 256);
+}
+
 static int br_variant()
 {
     static int v = -1;
@@ -999,6 +1321,8 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         cudaFuncSetAttribute(k_blind_rotate_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v5<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<5>::kSmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v5<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<6>::kSmemBytes);
         attr = true;
     }
     const int grid = (count + kBrGroups - 1) / kBrGroups;
@@ -1019,7 +1343,7 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         return;
     }
     // a last partial wave of at most two ciphertexts per SM also goes to the team kernel (3.2 / 2.4 ms instead of 5.8 ms)
-    if (br_variant() >= 3 && ll_mode == 1) {
+    if ((br_variant() == 3 || br_variant() == 4) && ll_mode == 1) {
         const int wave = ll_sms[attr_dev & 63] * kBrGroups, rem = count % wave;
         if (count > wave && rem > 0 && rem <= kLlTeams * ll_sms[attr_dev & 63]) {
             const int head = count - rem;
@@ -1027,6 +1351,20 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
             launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, rem);
             return;
         }
+    }
+    if (br_variant() == 5 || br_variant() == 6) {
+        // v5: twiddles in tensor memory, 5 or 6 groups per SM; a last partial wave of at most two ciphertexts per SM
+        // goes to the team kernel
+        const int G = br_variant(), wave = ll_sms[attr_dev & 63] * G;
+        int head = count;
+        const int rem = count % wave;
+        if (ll_mode == 1 && count > wave && rem > 0 && rem <= kLlTeams * ll_sms[attr_dev & 63]) head = count - rem;
+        if (G == 5)
+            k_blind_rotate_v5<5><<<(head + 4) / 5, 64 * 5, Br5<5>::kSmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw);
+        else
+            k_blind_rotate_v5<6><<<(head + 5) / 6, 64 * 6, Br5<6>::kSmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw);
+        if (head < count) launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, count - head);
+        return;
     }
     if (br_variant() == 0)
         k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
