@@ -839,11 +839,10 @@ int cbs_trans_key_upload(cbs_ctx *ctx, const uint64_t *k10_9, const uint64_t *k8
 {
     ENTER(ctx);
     if (!k10_9 || !k8_1 || !k0) return set_error("cbs_trans_key_upload: null argument"), CBS_ERR_ARG;
-    if (!ctx->d_k10_9) {
-        CUDA_TRY(cudaMalloc(&ctx->d_k10_9, (size_t)CBS_K10_9_WORDS * 8));
-        CUDA_TRY(cudaMalloc(&ctx->d_k8_1, (size_t)CBS_K8_1_WORDS * 8));
-        CUDA_TRY(cudaMalloc(&ctx->d_k0, (size_t)CBS_K0_WORDS * 8));
-    }
+    // each buffer on its own: a failed allocation leaves its pointer null and the next call retries it
+    if (!ctx->d_k10_9) CUDA_TRY(cudaMalloc(&ctx->d_k10_9, (size_t)CBS_K10_9_WORDS * 8));
+    if (!ctx->d_k8_1) CUDA_TRY(cudaMalloc(&ctx->d_k8_1, (size_t)CBS_K8_1_WORDS * 8));
+    if (!ctx->d_k0) CUDA_TRY(cudaMalloc(&ctx->d_k0, (size_t)CBS_K0_WORDS * 8));
     TRY(upload(ctx, ctx->d_k10_9, k10_9, (size_t)CBS_K10_9_WORDS * 8));
     TRY(upload(ctx, ctx->d_k8_1, k8_1, (size_t)CBS_K8_1_WORDS * 8));
     TRY(upload(ctx, ctx->d_k0, k0, (size_t)CBS_K0_WORDS * 8));
@@ -880,11 +879,9 @@ int cbs_fwd_trans_key_upload(cbs_ctx *ctx, const uint64_t *kf_first, const uint6
 {
     ENTER(ctx);
     if (!kf_first || !kf_mid || !kf_last) return set_error("cbs_fwd_trans_key_upload: null argument"), CBS_ERR_ARG;
-    if (!ctx->d_kf_first) {
-        CUDA_TRY(cudaMalloc(&ctx->d_kf_first, (size_t)CBS_KF_FIRST_WORDS * 8));
-        CUDA_TRY(cudaMalloc(&ctx->d_kf_mid, (size_t)CBS_KF_MID_WORDS * 8));
-        CUDA_TRY(cudaMalloc(&ctx->d_kf_last, (size_t)CBS_KF_LAST_WORDS * 8));
-    }
+    if (!ctx->d_kf_first) CUDA_TRY(cudaMalloc(&ctx->d_kf_first, (size_t)CBS_KF_FIRST_WORDS * 8));
+    if (!ctx->d_kf_mid) CUDA_TRY(cudaMalloc(&ctx->d_kf_mid, (size_t)CBS_KF_MID_WORDS * 8));
+    if (!ctx->d_kf_last) CUDA_TRY(cudaMalloc(&ctx->d_kf_last, (size_t)CBS_KF_LAST_WORDS * 8));
     TRY(upload(ctx, ctx->d_kf_first, kf_first, (size_t)CBS_KF_FIRST_WORDS * 8));
     TRY(upload(ctx, ctx->d_kf_mid, kf_mid, (size_t)CBS_KF_MID_WORDS * 8));
     TRY(upload(ctx, ctx->d_kf_last, kf_last, (size_t)CBS_KF_LAST_WORDS * 8));

@@ -10,6 +10,7 @@
 // of a CTA drift freely and hide each other's shared-memory and barrier latency.
 #include "cbs_kernels.cuh"
 #include "fft512.cuh"
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -1118,7 +1119,7 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v5(const uint64_t *_
     using L = Br5<G>;
     constexpr int R = L::kRing;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6, warp = threadIdx.x >> 5;
+    const int gi = threadIdx.x >> 6, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ct = blockIdx.x * G + gi;
     unsigned char *ring = smem_raw + L::kRingOff;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L::kBarOff);
@@ -1128,7 +1129,7 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v5(const uint64_t *_
     if (threadIdx.x == 0) {
         for (int b = 0; b < R; b++) {
             mbar_init(full + b, 1);
-            mbar_init(empty + b, 64 * active_groups);
+            mbar_init(empty + b, 2 * active_groups);  // one arrive per WARP (32 same-address arrives serialise in the LSU)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1247,7 +1248,8 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v5(const uint64_t *_
                         const cplx *key = reinterpret_cast<const cplx *>(ring + buf * L::kPolyBytes) + t;
 #pragma unroll
                         for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[k3 * 64]);
-                        mbar_arrive(empty + buf);
+                        __syncwarp();  // every lane's tile reads have been consumed by the products above
+                        if (lane == 0) mbar_arrive(empty + buf);
                     }
                 } else {
                     if (producer) pump(tile + 3);
@@ -1256,7 +1258,7 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v5(const uint64_t *_
                     for (int c = 0; c < 3; c++, tile++) {
                         const int buf = tile % R;
                         mbar_wait(full + buf, (tile / R) & 1);
-                        mbar_arrive(empty + buf);
+                        if (lane == 0) mbar_arrive(empty + buf);
                     }
                 }
             }
@@ -1321,6 +1323,7 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         cudaFuncSetAttribute(k_blind_rotate_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v5<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<4>::kSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v5<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<5>::kSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v5<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<6>::kSmemBytes);
         attr = true;
@@ -1338,12 +1341,12 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         const int teams = n <= ll_sms[attr_dev & 63] ? 1 : kLlTeams;
         k_blind_rotate_ll<<<(n + teams - 1) / teams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(in, out, n, K.bsk_f, K.tw, teams);
     };
-    if (br_variant() >= 3 && (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * ll_sms[attr_dev & 63]))) {
+    if (br_variant() >= 3 && br_variant() != 4 && (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * ll_sms[attr_dev & 63]))) {
         launch_team(lwe, acc, count);
         return;
     }
     // a last partial wave of at most two ciphertexts per SM also goes to the team kernel (3.2 / 2.4 ms instead of 5.8 ms)
-    if ((br_variant() == 3 || br_variant() == 4) && ll_mode == 1) {
+    if (br_variant() == 3 && ll_mode == 1) {
         const int wave = ll_sms[attr_dev & 63] * kBrGroups, rem = count % wave;
         if (count > wave && rem > 0 && rem <= kLlTeams * ll_sms[attr_dev & 63]) {
             const int head = count - rem;
@@ -1351,6 +1354,10 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
             launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, rem);
             return;
         }
+    }
+    if (br_variant() == 4) {  // v5 code at 4 groups per SM (A/B against v3 at equal occupancy)
+        k_blind_rotate_v5<4><<<(count + 3) / 4, 64 * 4, Br5<4>::kSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+        return;
     }
     if (br_variant() == 5 || br_variant() == 6) {
         // v5: twiddles in tensor memory, 5 or 6 groups per SM; a last partial wave of at most two ciphertexts per SM
@@ -1369,14 +1376,13 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     if (br_variant() == 0)
         k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
     else {
-        static int split = -1, sms = 0;
-        if (split < 0) {
+        // CBS_BR_SPLIT is read once (thread-safe function-local static); the SM count is the per-device value above:
+        // the stage executables call this from one host thread per GPU
+        static const int split = [] {
             const char *e = getenv("CBS_BR_SPLIT");
-            split = e ? atoi(e) : 0;
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        }
+            return e ? atoi(e) : 0;
+        }();
+        const int sms = std::max(1, ll_sms[attr_dev & 63]);
         const int full_wave = sms * kBrGroups;
         const int rem = count % full_wave;
         const bool xch = br_variant() >= 3;

@@ -960,7 +960,8 @@ int cbs_lwe_list_load(const char *path, uint64_t **data, uint64_t *count, uint64
         return CBS_ERR_IO;
     }
     uint64_t n = r.u64();
-    if (!r.ok || r.off + 8 * n + 32 != r.buf.size()) {
+    // n comes from the file: bound it by the bytes actually present before any multiplication can wrap
+    if (!r.ok || r.buf.size() < r.off + 32 || n != (r.buf.size() - r.off - 32) / 8 || (r.buf.size() - r.off - 32) % 8) {
         set_error(std::string(path) + ": not an LweCiphertextList<u64>");
         return CBS_ERR_FORMAT;
     }

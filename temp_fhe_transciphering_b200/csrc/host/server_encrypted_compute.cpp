@@ -23,7 +23,7 @@ int main(int argc, char **argv)
 
     uint64_t *data = nullptr, count = 0, words = 0;
     STAGE_TRY(cbs_lwe_list_load((io_dir + "/ciphertext_aes_download/result.bin").c_str(), &data, &count, &words));
-    if (words != CBS_LWE_BIG_WORDS || count == 0 || count % 16 != 0) {
+    if (words != CBS_LWE_BIG_WORDS || count == 0 || count % 16 != 0 || count / 16 > (uint64_t)(1 << 24)) {
         fprintf(stderr, "Error: lwe_ciphertext_list length is not a multiple of 16\n");
         return 1;
     }
