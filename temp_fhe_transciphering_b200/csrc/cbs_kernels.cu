@@ -10,6 +10,7 @@
 // of a CTA drift freely and hide each other's shared-memory and barrier latency.
 #include "cbs_kernels.cuh"
 #include "fft512.cuh"
+#include "fftw512.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -1297,6 +1298,502 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v5(const uint64_t *_
     if (warp == 0) tmem_dealloc_cols(*tmem_slot, 256);
 }
 
+// ---- W: one warp per polynomial, one team of three warps per ciphertext -------------------------------------------------
+// (design notes in fftw512.cuh)  A CTA holds 4 ciphertexts.  Team q = warps q, q + 4, q + 8: they share lane quarter q
+// of tensor memory and scheduler q.  Warp r of a team owns accumulator polynomial r: it builds the digits of polynomial r
+// (16 points per thread), transforms them with shuffles only, parks the spectrum in TENSOR MEMORY where its two team
+// mates read it (same lane, other warp: the one exchange pattern tcgen05.ld/st offers across warps), accumulates output
+// column r against the three BSK row tiles of the step, inverse-transforms and updates polynomial r - which no other
+// warp ever touches, so the accumulator needs no cross-warp synchronisation at all.  Per step a team executes two 96-thread
+// barriers (spectra published / spectra consumed) where k_blind_rotate_v3 executes six 64-thread barriers per group
+// plus the lock-step of 12 transposes through shared memory.  Shared memory holds only the accumulators (24 KB per
+// ciphertext) and a FIVE-row ring of BSK tiles; the per-lane transform tables (160 words) sit in tensor memory.
+constexpr int kWTeams = 4;
+constexpr int kWRing = 5;                                     // ring depth in BSK rows (24,576 B each)
+constexpr int kWRingOff = kWTeams * kGlweWords * 8;           // 98,304
+constexpr int kWBarOff = kWRingOff + kWRing * kBrTileBytes;   // 221,184
+constexpr int kWRotOff = kWBarOff + 2 * kWRing * 8 + 16;
+constexpr int kWSmemBytes = kWRotOff + kWTeams * kLweN * 2;   // 227,424
+constexpr int kWSpecCol = 4 * kWTabCplx;                      // tensor-memory columns: tables [0, 160), spectra 160 + 64 r
+
+// four complex doubles <-> 16 tensor-memory columns of this thread's lane.  The 32-bit halves are packed / unpacked INSIDE the
+// asm block (mov.b64), where ptxas coalesces them with the 64-bit registers: formed with __hiloint2double outside, every
+// double cost an IMAD.MOV (ncu r02_br_w1: 9 % of all instructions were such moves).
+__device__ __forceinline__ void tmem_ld_c4(uint32_t taddr, cplx *w)
+{
+    asm volatile(
+        "{\n\t.reg .b32 t<16>;\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n\t"
+        "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t"
+        "mov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t}"
+        : "=d"(w[0].x), "=d"(w[0].y), "=d"(w[1].x), "=d"(w[1].y), "=d"(w[2].x), "=d"(w[2].y), "=d"(w[3].x), "=d"(w[3].y)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_c4d(uint32_t taddr, const cplx *w)
+{
+    asm volatile(
+        "{\n\t.reg .b32 t<16>;\n\t"
+        "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\t"
+        "mov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\t"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15};\n\t}" ::"r"(taddr),
+        "d"(w[0].x), "d"(w[0].y), "d"(w[1].x), "d"(w[1].y), "d"(w[2].x), "d"(w[2].y), "d"(w[3].x), "d"(w[3].y)
+        : "memory");
+}
+struct TmemTab {
+    uint32_t base;
+    __device__ __forceinline__ void get4(int first, cplx *w) const { tmem_ld_c4(base + 4 * first, w); }
+};
+struct GlobalTab {
+    const double *p;
+    __device__ __forceinline__ void get4(int first, cplx *w) const
+    {
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = ldg_cplx(p + (size_t)(first + k) * 2);
+    }
+};
+
+// standard -> Fourier conversion into the W layout: out[poly][rho][lane] = TRUE bin wbin(lane, rho) / 512
+__global__ void __launch_bounds__(128) k_std_to_fourier_w(const uint64_t *__restrict__ in, double *__restrict__ out, int npoly,
+                                                           const double *__restrict__ wtab)
+{
+    const int lane = threadIdx.x & 31;
+    const int poly = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (poly >= npoly) return;
+    const GlobalTab tab{wtab + (size_t)lane * kWTabCplx * 2};
+    const uint64_t *p = in + (size_t)poly * 1024;
+    cplx v[16];
+#pragma unroll
+    for (int m = 0; m < 16; m++) v[m] = cplx{torus_to_double(p[lane + 32 * m]), torus_to_double(p[lane + 32 * m + 512])};
+    wfwd_s1(v, tab);
+    wexchange_a<-1>(v, lane);
+    wfwd_s2(v, tab);
+    wexchange_b<-1>(v, lane);
+    wfwd_s3(v);
+    double *o = out + (size_t)poly * kFourierPolyDoubles;
+#pragma unroll
+    for (int rho = 0; rho < 16; rho++) {
+        // the transform leaves conj(phi) * X with phi = W4^e = (-i)^e: multiply by phi
+        const int e = wphase_exp(lane, rho);
+        cplx x = v[rho];
+        if (e == 1) x = cplx{v[rho].y, -v[rho].x};
+        else if (e == 2) x = cplx{-v[rho].x, -v[rho].y};
+        else if (e == 3) x = cplx{-v[rho].y, v[rho].x};
+        *reinterpret_cast<double2 *>(o + (size_t)(rho * 32 + lane) * 2) = make_double2(x.x * (1.0 / 512.0), x.y * (1.0 / 512.0));
+    }
+}
+
+void launch_std_to_fourier_w(const uint64_t *in, double *out, int npoly, const double *wtab, cudaStream_t s)
+{
+    if (npoly <= 0) return;
+    k_std_to_fourier_w<<<(npoly + 3) / 4, 128, 0, s>>>(in, out, npoly, wtab);
+}
+
+__global__ void __launch_bounds__(96 * kWTeams, 1) k_blind_rotate_w(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out,
+                                                                     int count, const double *__restrict__ bsk_w,
+                                                                     const double *__restrict__ wtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, r = warp >> 2;  // team (lane quarter), polynomial / output column of this warp
+    const int ct = blockIdx.x * kWTeams + q;
+    unsigned char *ring = smem_raw + kWRingOff;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kWBarOff);
+    uint64_t *empty = full + kWRing;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + kWRing);
+    const int active_teams = min(kWTeams, count - blockIdx.x * kWTeams);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kWRing; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, 3 * active_teams);  // one arrive per warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc_cols(tmem_slot, 512);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tq = *tmem_slot + ((uint32_t)(32 * q) << 16);  // lane quarter q, column 0
+    if (r == 0) {  // the tables depend on the lane only: one copy per lane quarter, shared by the three warps of the team
+        const double *src = wtab + (size_t)lane * kWTabCplx * 2;
+        for (int e = 0; e < kWTabCplx; e += 4) {
+            cplx w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] = ldg_cplx(src + (size_t)(e + k) * 2);
+            tmem_st_c4(tq + 4 * e, w);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (ct < count) {
+        const TmemTab tab{tq};
+        const bool producer = (threadIdx.x == 0);
+        const char *bsk_bytes = reinterpret_cast<const char *>(bsk_w);
+        constexpr int kTiles = kLweN * 3;
+        if (producer)
+            for (int b = 0; b < kWRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
+        __syncwarp();
+        u64x2 *p = reinterpret_cast<u64x2 *>(smem_raw + (size_t)q * kGlweWords * 8) + r * 512;  // polynomial r as pairs (j, j + 512)
+        const int tbar = 1 + q;
+        const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+        uint16_t *rot = reinterpret_cast<uint16_t *>(smem_raw + kWRotOff) + q * kLweN;
+        for (int i = lane + 32 * r; i < kLweN; i += 96) rot[i] = (uint16_t)(modswitch_dev(a[i]) & 2047);
+        {
+            const int bt = modswitch_dev(a[kLweN]);
+            for (int jj = lane; jj < 512; jj += 32) {
+                u64x2 b{0, 0};
+                if (r == 2) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int j = jj + 512 * h;
+                        const int e = (j + bt) & 2047;
+                        const int i = e & 1023;
+                        uint64_t val = 1ull << (61 - 2 * (i & 7));
+                        const bool neg = (i < 512) != ((e & 1024) != 0);
+                        (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
+                    }
+                }
+                p[jj] = b;
+            }
+        }
+        named_sync(tbar, 96);
+
+        int next_fill = kWRing;
+        auto pump = [&](int need_upto) {
+            while (next_fill < kTiles) {
+                const int sl = next_fill % kWRing, prev_use = next_fill / kWRing - 1;
+                if (next_fill < need_upto) mbar_wait(empty + sl, prev_use & 1);
+                else if (!mbar_test(empty + sl, prev_use & 1)) break;
+                tma_load_tile(ring + sl * kBrTileBytes, bsk_bytes + (size_t)next_fill * kBrTileBytes, kBrTileBytes, full + sl);
+                next_fill++;
+            }
+        };
+        bool spectra_in_use = false;  // the previous step's spectra may still be read by a team mate
+#pragma unroll 1
+        for (int i = 0; i < kLweN; i++) {
+            const int d = rot[i];
+            const int t0 = 3 * i;
+            if (producer) pump(0);
+            __syncwarp();
+            if (d == 0) {  // trivial rotation: the product is exactly zero (pbs.rs:111); only the ring bookkeeping remains
+                if (producer) pump(t0 + 3);
+                __syncwarp();
+#pragma unroll 1
+                for (int rr = 0; rr < 3; rr++) {
+                    const int tile = t0 + rr;
+                    mbar_wait(full + tile % kWRing, (tile / kWRing) & 1);
+                    if (lane == 0) mbar_arrive(empty + tile % kWRing);
+                }
+                continue;
+            }
+            cplx v[16];
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const int jj = lane + 32 * m;
+                const int e0 = (jj - d) & 2047;
+                const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];
+                const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
+                const bool sw = (e0 & 512) != 0;
+                const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
+                const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
+                const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
+                const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
+                v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
+                            digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
+            }
+            wfwd_s1(v, tab);
+            wexchange_a<-1>(v, lane);
+            wfwd_s2(v, tab);
+            wexchange_b<-1>(v, lane);
+            wfwd_s3(v);
+            if (producer) pump(t0 + 3);
+            __syncwarp();
+            // own product: column r of row r
+            cplx out[16];
+            {
+                const int tile = t0 + r;
+                mbar_wait(full + tile % kWRing, (tile / kWRing) & 1);
+                const cplx *key = reinterpret_cast<const cplx *>(ring + (tile % kWRing) * kBrTileBytes) + r * 512 + lane;
+#pragma unroll
+                for (int k = 0; k < 16; k++) out[k] = cmul(v[k], key[k * 32]);
+            }
+            // publish the spectrum in tensor memory
+            if (spectra_in_use) named_sync(tbar, 96);  // every team mate has finished reading the previous step's spectra
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) tmem_st_c4d(tq + kWSpecCol + 64 * r + 16 * c4, v + 4 * c4);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            named_sync(tbar, 96);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            spectra_in_use = true;
+#pragma unroll
+            for (int s = 1; s < 3; s++) {
+                const int rr = (r + s) % 3;
+                const int tile = t0 + rr;
+                mbar_wait(full + tile % kWRing, (tile / kWRing) & 1);
+                const cplx *key = reinterpret_cast<const cplx *>(ring + (tile % kWRing) * kBrTileBytes) + r * 512 + lane;
+                const TmemTab spec{tq + kWSpecCol + 64 * rr};
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) {
+                    cplx w[4];
+                    spec.get4(4 * c4, w);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) cfma(out[4 * c4 + k], w[k], key[(4 * c4 + k) * 32]);
+                }
+            }
+            __syncwarp();  // every lane's tile reads have been consumed by the products above
+            if (lane == 0) {
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) mbar_arrive(empty + (t0 + rr) % kWRing);
+            }
+            winv_s3(out);
+            wexchange_b<1>(out, lane);
+            winv_s2(out, tab);
+            wexchange_a<1>(out, lane);
+            winv_s1(out, tab);
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                u64x2 w = p[lane + 32 * m];
+                w.lo += torus_from_scaled(out[m].x);
+                w.hi += torus_from_scaled(out[m].y);
+                p[lane + 32 * m] = w;
+            }
+            __syncwarp();  // polynomial r is complete before this warp's next rotated reads
+        }
+        uint64_t *o = acc_out + (size_t)ct * kGlweWords + r * 1024;
+        for (int w = lane; w < 512; w += 32) {
+            const u64x2 x = p[w];
+            o[w] = x.lo;
+            o[w + 512] = x.hi;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 512);
+}
+
+// ---- W1: one warp per CIPHERTEXT, eight free-running warps per SM ---------------------------------------------------------
+// ncu on k_blind_rotate_w (profiles/r02_br_w1_ncu.csv): the three warps of a team share a scheduler and run in lock step
+// (two team barriers per step), so their FP64-heavy phases collide (math_pipe_throttle 1.1 per issue) and their integer
+// phases leave the FP64 pipe idle: 47 % FP64 utilisation, no better than k_blind_rotate_v3.  Here a warp owns a whole
+// ciphertext: no barrier of any kind, no cross-warp data, the eight warps of a CTA drift freely and interleave their
+// integer and FP64 phases on each scheduler.  What made one-warp-per-ciphertext impossible before is the register file:
+// three output columns of 16 complex points are 192 registers.  Column 0 stays in registers; columns 1 and 2 are
+// accumulated through TENSOR MEMORY (read-modify-write of 4 complex values at a time), which also holds the per-lane
+// transform tables.  Shared memory: 8 accumulators (192 KB) and a ring of four single-polynomial BSK tiles.
+constexpr int kW1Warps = 8;
+constexpr int kW1Ring = 4;
+constexpr int kW1PolyBytes = 512 * 16;
+constexpr int kW1RingOff = kW1Warps * kGlweWords * 8;                  // 196,608
+constexpr int kW1BarOff = kW1RingOff + kW1Ring * kW1PolyBytes;         // 229,376
+constexpr int kW1SmemBytes = kW1BarOff + 2 * kW1Ring * 8 + 16;         // 229,456
+constexpr int kW1OutCol = 4 * kWTabCplx;                               // tensor-memory columns 160 + 128 h: columns 1, 2 of warp h
+
+__global__ void __launch_bounds__(32 * kW1Warps, 1) k_blind_rotate_w1(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out,
+                                                                       int count, const double *__restrict__ bsk_w,
+                                                                       const double *__restrict__ wtab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int ct = blockIdx.x * kW1Warps + warp;
+    unsigned char *ring = smem_raw + kW1RingOff;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kW1BarOff);
+    uint64_t *empty = full + kW1Ring;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + kW1Ring);
+    const int active_warps = min(kW1Warps, count - blockIdx.x * kW1Warps);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kW1Ring; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, active_warps);  // one arrive per warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc_cols(tmem_slot, 512);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tq = *tmem_slot + ((uint32_t)(32 * q) << 16);
+    if (h == 0) {  // one copy of the per-lane tables per lane quarter
+        const double *src = wtab + (size_t)lane * kWTabCplx * 2;
+        for (int e = 0; e < kWTabCplx; e += 4) {
+            cplx w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] = ldg_cplx(src + (size_t)(e + k) * 2);
+            tmem_st_c4d(tq + 4 * e, w);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (ct < count) {
+        const TmemTab tab{tq};
+        const uint32_t tout = tq + kW1OutCol + 128 * h;  // column c (1 or 2) at tout + 64 (c - 1)
+        const bool producer = (threadIdx.x == 0);
+        const char *bsk_bytes = reinterpret_cast<const char *>(bsk_w);
+        constexpr int kTiles = kLweN * 9;
+        if (producer)
+            for (int b = 0; b < kW1Ring; b++) tma_load_tile(ring + b * kW1PolyBytes, bsk_bytes + (size_t)b * kW1PolyBytes, kW1PolyBytes, full + b);
+        __syncwarp();
+        u64x2 *acc = reinterpret_cast<u64x2 *>(smem_raw + (size_t)warp * kGlweWords * 8);  // [3][512] pairs (j, j + 512)
+        const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+        {
+            const int bt = modswitch_dev(a[kLweN]);
+            for (int jj = lane; jj < 512; jj += 32) {
+                u64x2 b;
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const int j = jj + 512 * hh;
+                    const int e = (j + bt) & 2047;
+                    const int i = e & 1023;
+                    uint64_t val = 1ull << (61 - 2 * (i & 7));
+                    const bool neg = (i < 512) != ((e & 1024) != 0);
+                    (hh ? b.hi : b.lo) = neg ? (0ull - val) : val;
+                }
+                acc[jj] = u64x2{0, 0};
+                acc[512 + jj] = u64x2{0, 0};
+                acc[1024 + jj] = b;
+            }
+        }
+        __syncwarp();
+        int next_fill = kW1Ring;
+        auto pump = [&](int need_upto) {
+            while (next_fill < kTiles) {
+                const int sl = next_fill % kW1Ring, prev_use = next_fill / kW1Ring - 1;
+                if (next_fill < need_upto) mbar_wait(empty + sl, prev_use & 1);
+                else if (!mbar_test(empty + sl, prev_use & 1)) break;
+                tma_load_tile(ring + sl * kW1PolyBytes, bsk_bytes + (size_t)next_fill * kW1PolyBytes, kW1PolyBytes, full + sl);
+                next_fill++;
+            }
+        };
+        uint64_t a_next = __ldg(a);  // mask word of the next step, fetched one step ahead
+        int tile = 0;
+#pragma unroll 1
+        for (int i = 0; i < kLweN; i++) {
+            const int d = modswitch_dev(a_next) & 2047;
+            a_next = __ldg(a + min(i + 1, kLweN - 1));
+            if (d == 0) {  // trivial rotation: the external product is exactly zero (pbs.rs:111); ring bookkeeping only
+#pragma unroll 1
+                for (int k = 0; k < 9; k++, tile++) {
+                    if (producer) pump(tile + 1);
+                    __syncwarp();
+                    mbar_wait(full + tile % kW1Ring, (tile / kW1Ring) & 1);
+                    if (lane == 0) mbar_arrive(empty + tile % kW1Ring);
+                }
+                continue;
+            }
+            cplx out0[16];
+#pragma unroll 1
+            for (int r = 0; r < 3; r++) {
+                if (producer) pump(0);
+                __syncwarp();
+                cplx v[16];
+                const u64x2 *p = acc + r * 512;
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    const int jj = lane + 32 * m;
+                    const int e0 = (jj - d) & 2047;
+                    const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];
+                    const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
+                    const bool sw = (e0 & 512) != 0;
+                    const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
+                    const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
+                    const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
+                    const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
+                    v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
+                                digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
+                }
+                wfwd_s1(v, tab);
+                wexchange_a<-1>(v, lane);
+                if (producer) pump(0);
+                __syncwarp();
+                wfwd_s2(v, tab);
+                wexchange_b<-1>(v, lane);
+                wfwd_s3(v);
+                // column 0: registers
+                {
+                    if (producer) pump(tile + 1);
+                    __syncwarp();
+                    mbar_wait(full + tile % kW1Ring, (tile / kW1Ring) & 1);
+                    const cplx *key = reinterpret_cast<const cplx *>(ring + (tile % kW1Ring) * kW1PolyBytes) + lane;
+                    if (r == 0) {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) out0[k] = cmul(v[k], key[k * 32]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) cfma(out0[k], v[k], key[k * 32]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + tile % kW1Ring);
+                    tile++;
+                }
+                // columns 1 and 2: accumulated through tensor memory, four complex values at a time
+#pragma unroll
+                for (int c = 1; c < 3; c++, tile++) {
+                    if (producer) pump(tile + 1);
+                    __syncwarp();
+                    mbar_wait(full + tile % kW1Ring, (tile / kW1Ring) & 1);
+                    const cplx *key = reinterpret_cast<const cplx *>(ring + (tile % kW1Ring) * kW1PolyBytes) + lane;
+                    const uint32_t tc = tout + 64 * (c - 1);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        cplx w[4];
+                        if (r == 0) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) w[k] = cmul(v[4 * c4 + k], key[(4 * c4 + k) * 32]);
+                        } else {
+                            tmem_ld_c4(tc + 16 * c4, w);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) cfma(w[k], v[4 * c4 + k], key[(4 * c4 + k) * 32]);
+                        }
+                        tmem_st_c4d(tc + 16 * c4, w);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + tile % kW1Ring);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // before the next row reads the partial sums back
+            }
+#pragma unroll 1
+            for (int c = 0; c < 3; c++) {
+                if (c > 0) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) tmem_ld_c4(tout + 64 * (c - 1) + 16 * c4, out0 + 4 * c4);
+                }
+                winv_s3(out0);
+                wexchange_b<1>(out0, lane);
+                if (producer) pump(0);
+                __syncwarp();
+                winv_s2(out0, tab);
+                wexchange_a<1>(out0, lane);
+                winv_s1(out0, tab);
+                u64x2 *p = acc + c * 512;
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    u64x2 w = p[lane + 32 * m];
+                    w.lo += torus_from_scaled(out0[m].x);
+                    w.hi += torus_from_scaled(out0[m].y);
+                    p[lane + 32 * m] = w;
+                }
+            }
+            __syncwarp();  // the accumulator is complete before the next step's rotated reads
+        }
+        uint64_t *o = acc_out + (size_t)ct * kGlweWords;
+        for (int w = lane; w < 3 * 512; w += 32) {
+            const u64x2 x = acc[w];
+            const int c = w >> 9, jj = w & 511;
+            o[c * 1024 + jj] = x.lo;
+            o[c * 1024 + jj + 512] = x.hi;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 512);
+}
+
 static int br_variant()
 {
     static int v = -1;
@@ -1323,6 +1820,8 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         cudaFuncSetAttribute(k_blind_rotate_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_w, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_w1, cudaFuncAttributeMaxDynamicSharedMemorySize, kW1SmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v5<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<4>::kSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v5<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<5>::kSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v5<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<6>::kSmemBytes);
@@ -1341,7 +1840,7 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         const int teams = n <= ll_sms[attr_dev & 63] ? 1 : kLlTeams;
         k_blind_rotate_ll<<<(n + teams - 1) / teams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(in, out, n, K.bsk_f, K.tw, teams);
     };
-    if (br_variant() >= 3 && br_variant() != 4 && (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * ll_sms[attr_dev & 63]))) {
+    if (br_variant() >= 3 && br_variant() != 4 && br_variant() != 7 && br_variant() != 8 && (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * ll_sms[attr_dev & 63]))) {
         launch_team(lwe, acc, count);
         return;
     }
@@ -1354,6 +1853,24 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
             launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, rem);
             return;
         }
+    }
+    if (br_variant() == 7 && K.bsk_w) {  // W: team of three warps per ciphertext, 4 ciphertexts per SM
+        const int wave = ll_sms[attr_dev & 63] * kWTeams;
+        int head = count;
+        const int rem = count % wave;
+        if (ll_mode == 1 && count > wave && rem > 0 && rem <= ll_sms[attr_dev & 63]) head = count - rem;  // one per SM: team kernel
+        k_blind_rotate_w<<<(head + kWTeams - 1) / kWTeams, 96 * kWTeams, kWSmemBytes, s>>>(lwe, acc, head, K.bsk_w, K.wtab);
+        if (head < count) launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, count - head);
+        return;
+    }
+    if (br_variant() == 8 && K.bsk_w) {  // W1: one warp per ciphertext, 8 per SM
+        const int wave = ll_sms[attr_dev & 63] * kW1Warps;
+        int head = count;
+        const int rem = count % wave;
+        if (ll_mode == 1 && count > wave && rem > 0 && rem <= kLlTeams * ll_sms[attr_dev & 63]) head = count - rem;
+        k_blind_rotate_w1<<<(head + kW1Warps - 1) / kW1Warps, 32 * kW1Warps, kW1SmemBytes, s>>>(lwe, acc, head, K.bsk_w, K.wtab);
+        if (head < count) launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, count - head);
+        return;
     }
     if (br_variant() == 4) {  // v5 code at 4 groups per SM (A/B against v3 at equal occupancy)
         k_blind_rotate_v5<4><<<(count + 3) / 4, 64 * 4, Br5<4>::kSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);

@@ -342,7 +342,9 @@ def test_golden_pin_b_on_gpu(cbs):
     """Golden pin B (oracle/pin_against_reference.py): the UNMODIFIED reference stage-7 binary was run on inputs that are a
     pure function of two seeds; its decrypted bytes and per-bit phase errors are committed in
     tests/golden/reference_pin.json.  Regenerate the same inputs here, run cbs_aes128_transcipher on them and compare
-    with what the reference produced: same bytes, output noise std within 0.5 bit, worst bit within 1 bit."""
+    with what the reference produced: same bytes, output noise std at most 0.5 bit above the reference's (and not more than
+    1 bit below: 128 samples, and the CUDA path's FP64 transforms are a little quieter than concrete-fft's), worst bit
+    within 1 bit."""
     import json
     import os
     import aes_clear
@@ -363,7 +365,7 @@ def test_golden_pin_b_on_gpu(cbs):
     bits, std, mx = ref_io.noise_stats(got, ks.glwe_sk)
     ref = pin["reference_stage7"]
     assert np.packbits(bits).tobytes().hex() == ref["bytes_hex"] == pin["plaintext_hex"]
-    assert abs(std - ref["noise_log2_std"]) < 0.5, (std, ref["noise_log2_std"])
+    assert ref["noise_log2_std"] - 1.0 < std < ref["noise_log2_std"] + 0.5, (std, ref["noise_log2_std"])
     assert mx < ref["noise_log2_max"] + 1.0, (mx, ref["noise_log2_max"])
     # the reference's own per-bit errors: same scale, no bit of ours further out than the reference's worst by 2x
     ref_err = np.array(ref["phase_error_int64"], dtype=np.float64)
