@@ -501,25 +501,6 @@ int cbs_ctx_create(const cbs_keyset *ks, int device, cbs_ctx **out)
         cudaFree(d_tmp);
         return fail(rc);
     }
-    // second copy of the bsk in the bin order of the one-warp transform (fftw512.cuh), from the same staged words
-    {
-        std::vector<double> wtab = make_w_tables();
-        void *d_wtab, *d_bsk_w;
-        if ((rc = key_alloc(ctx, wtab.size() * 8, &d_wtab)) || (rc = key_alloc(ctx, (size_t)CBS_BSK_WORDS * 8, &d_bsk_w)) ||
-            (rc = upload(ctx, d_wtab, wtab.data(), wtab.size() * 8))) {
-            cudaFree(d_tmp);
-            return fail(rc);
-        }
-        launch_std_to_fourier_w((const uint64_t *)d_tmp, (double *)d_bsk_w, CBS_BSK_WORDS / 1024, (const double *)d_wtab, ctx->stream);
-        ctx->launches++;
-        if ((rc = check_launch("k_std_to_fourier_w"))) {
-            cudaFree(d_tmp);
-            return fail(rc);
-        }
-        cudaStreamSynchronize(ctx->stream);  // wtab (host) goes out of scope
-        ctx->K.wtab = (const double *)d_wtab;
-        ctx->K.bsk_w = (const double *)d_bsk_w;
-    }
     // ss key (:665-687)
     if ((rc = conv(ks->ss.data(), CBS_SS_WORDS, (double *)d_ss_f, 0))) {
         cudaFree(d_tmp);

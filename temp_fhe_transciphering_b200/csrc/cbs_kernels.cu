@@ -10,10 +10,10 @@
 // of a CTA drift freely and hide each other's shared-memory and barrier latency.
 #include "cbs_kernels.cuh"
 #include "fft512.cuh"
-#include "fftw512.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 namespace cbs {
 
@@ -313,11 +313,7 @@ void launch_lwe_keyswitch(const DeviceKeys &K, const uint64_t *in, uint64_t *out
 // One group per LWE ciphertext, kBrGroups groups per CTA, 1 CTA per SM.  Per step:
 //   3 x [rotate-subtract + decompose + forward FFT]  ->  9 pointwise MACs against BSK_i  ->
 //   3 x [inverse FFT + torus rounding + accumulate].
-// BSK_i (73,728 B) is read once per group per step with 16-byte coalesced loads; the groups of a
-// CTA walk the key in near lock-step so all but the first read hit L1/L2.
 constexpr int kBrGroups = 4;
-constexpr int kBrGroupSmem = kGlweWords * 8 + 2 * 512 * 16;  // 24 KB accumulator + 2 x 8 KB tiles
-constexpr int kBrSmemBytes = kBrGroups * kBrGroupSmem;
 
 __device__ __forceinline__ int modswitch_dev(uint64_t x)
 {
@@ -325,85 +321,6 @@ __device__ __forceinline__ int modswitch_dev(uint64_t x)
     uint64_t y = x >> 55;
     y = (y + 1) >> 1;
     return (int)(y << 3);
-}
-
-__global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate(const uint64_t *__restrict__ lwe,
-                                                                     uint64_t *__restrict__ acc_out, int count,
-                                                                     const double *__restrict__ bsk_f,
-                                                                     const double *__restrict__ twtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6;
-    const int ct = blockIdx.x * kBrGroups + gi;
-    if (ct >= count) return;
-    unsigned char *base = smem_raw + (size_t)gi * kBrGroupSmem;
-    uint64_t *acc = reinterpret_cast<uint64_t *>(base);
-    Group g;
-    g.t = threadIdx.x & 63;
-    g.bar = 1 + gi;
-    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
-    g.scr1 = g.scr0 + 512;
-    g.flip = 0;
-    Twiddles tw;
-    load_twiddles(tw, twtab, g.t);
-    const uint64_t *a = lwe + (size_t)ct * kLweSmall;
-    const int t = g.t;
-
-    // acc = (0, 0, A * X^{-b~}),  A[i] = -+2^(61 - 2*(i%8))  (negative for i < 512)
-    {
-        const int bt = modswitch_dev(a[kLweN]);
-        for (int j = t; j < 1024; j += 64) {
-            acc[j] = 0;
-            acc[1024 + j] = 0;
-            const int e = (j + bt) & 2047;
-            const int i = e & 1023;
-            uint64_t val = 1ull << (61 - 2 * (i & 7));
-            const bool neg = (i < 512) != ((e & 1024) != 0);
-            acc[2048 + j] = neg ? (0ull - val) : val;
-        }
-    }
-    group_sync(g.bar);
-
-    for (int i = 0; i < kLweN; i++) {
-        const int d = modswitch_dev(__ldg(a + i)) & 2047;
-        if (d == 0) continue;  // ct1 == 0: the external product adds exactly zero (pbs.rs:111)
-        const double *bsk_i = bsk_f + (size_t)i * 9 * kFourierPolyDoubles;
-        cplx out[3][8];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
-#pragma unroll 1
-        for (int r = 0; r < 3; r++) {
-            const uint64_t *p = acc + r * 1024;
-            cplx v[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int j = t + 64 * m;
-                const int e = (j - d) & 2047;
-                uint64_t xl = neg_read(p, e) - p[j];
-                uint64_t xh = neg_read(p, (e + 512) & 2047) - p[j + 512];
-                uint64_t sl = decomp_init(xl, 23, 1), sh = decomp_init(xh, 23, 1);
-                v[m] = cplx{i32_to_double(decomp_next(sl, 23)), i32_to_double(decomp_next(sh, 23))};
-            }
-            fwd_fft(v, g, tw);
-            mul_acc<3>(out, v, bsk_i + (size_t)r * 3 * kFourierPolyDoubles, t);
-        }
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            inv_fft(out[c], g, tw);
-            uint64_t *p = acc + c * 1024;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int j = t + 64 * m;
-                p[j] += torus_from_scaled(out[c][m].x);
-                p[j + 512] += torus_from_scaled(out[c][m].y);
-            }
-        }
-    }
-    group_sync(g.bar);
-    uint64_t *o = acc_out + (size_t)ct * kGlweWords;
-    for (int j = t; j < kGlweWords; j += 64) o[j] = acc[j];
 }
 
 // ---- key tiles through a bulk-copy (TMA) ring ------------------------------------------------------------
@@ -473,14 +390,8 @@ __device__ __forceinline__ void tma_load_tile(void *dst, const void *src, uint32
 //     last forward pass.
 // (Tried and rejected on B200: pass-2 twiddles in a shared table, 13.3 vs 12.4 ms; three polynomials in
 //  flight per group with 3 groups per CTA, 18.5 ms: occupancy beats per-thread ILP here.)
-__device__ __forceinline__ int32_t digit_b23_l1(uint64_t x)
-{
-    // tfhe SignedDecomposer(23, 1): closest representable, balanced digit in (-2^22, 2^22]
-    const uint32_t s = (((uint32_t)(x >> 40)) + 1u) >> 1;  // round(x / 2^41) in [0, 2^23]
-    return (int32_t)s - ((s > (1u << 22)) ? (1 << 23) : 0);
-}
-
-// The same digit from the high word of x only, directly as a double.  With hi = x >> 32:
+// tfhe SignedDecomposer(23, 1) digit (closest representable, balanced, in (-2^22, 2^22]) from the high word of x only,
+// directly as a double.  With hi = x >> 32:
 //   s = ((hi >> 8) + 1) >> 1,  digit = s - (s > 2^22 ? 2^23 : 0)   ==   (((int32)(hi - 0x100)) >> 9) + 1
 // (digit_b23_l1_hi in fft512.cuh, checked against the generic decomposer in tests/cpu_emul); digit + 2^31 is the low word of the magic
 // number 2^52 + 2^31 + digit, so the conversion is three integer instructions and one DADD.
@@ -531,17 +442,7 @@ __device__ __forceinline__ void inv_p2_s(cplx v[8], cplx *scr, const cplx *t2s, 
     for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
 }
 
-// whole transforms with the pass-2 twiddles in shared memory (t2s = table[k2*8 + t'] + (t & 7))
-__device__ __forceinline__ void fwd_fft_s(cplx v[8], Group &g, const Twiddles &tw, const cplx *t2s)
-{
-    cplx *s = g.flip ? g.scr1 : g.scr0;
-    g.flip ^= 1;
-    fwd_p1(v, s, tw, g.t);
-    group_sync(g.bar);
-    fwd_p2_s(v, s, t2s, g.t);
-    group_sync(g.bar);
-    fwd_p3(v, s, g.t);
-}
+// inverse transform with the pass-2 twiddles in shared memory (t2s = table[k2*8 + t'] + (t & 7))
 __device__ __forceinline__ void inv_fft_s(cplx v[8], Group &g, const Twiddles &tw, const cplx *t2s)
 {
     cplx *s = g.flip ? g.scr1 : g.scr0;
@@ -591,28 +492,18 @@ __device__ __forceinline__ void fill_t2_table(cplx *t2tab, const double *twtab, 
 constexpr int kBr3GroupSmem = kGlweWords * 8 + 2 * 512 * 16;                         // 40 KB
 constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes + 64 + kBrGroups * kLweN * 2;  // + mbarriers + rotations
 
-// XCH = true ("v4"): the pass-2 <-> pass-3 transposes of all six transforms go through width-8 warp shuffles
-// (fft512.cuh, shuffle-exchange variant) instead of shared memory: 432 fewer shared-memory wavefronts per
-// step and ciphertext (ncu: the shared-memory data pipe, not FP64, is the busiest unit of v3) and 6 instead
-// of 12 group barriers per step.  The BSK stays in the plain transform's layout.
+// The pass-2 <-> pass-3 transposes of all six transforms go through width-8 warp shuffles (fft512.cuh,
+// shuffle-exchange variant) instead of shared memory: 432 fewer shared-memory wavefronts per step and
+// ciphertext (ncu r01: the shared-memory data pipe, not FP64, was the busiest unit) and 6 instead of 12 group
+// barriers per step.  The BSK stays in the plain transform's layout.
 // (Tried and rejected: a producer lane that polls the ring's `empty` barriers with mbarrier.test_wait at four points of
 //  every polynomial instead of blocking at the top of it: 6.04 vs 5.83 ms per wave.)
-template <bool PROF, bool XCH>
 __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uint64_t *__restrict__ lwe,
                                                                         uint64_t *__restrict__ acc_out, int count,
                                                                         const double *__restrict__ bsk_f,
                                                                         const double *__restrict__ twtab, int groups,
-                                                                        int ct_base, unsigned long long *prof)
+                                                                        int ct_base)
 {
-    // PROF: per-phase clock64() totals of thread 0 of CTA 0 (development aid, CBS_BR_PROF=1)
-    long long pc[6] = {0, 0, 0, 0, 0, 0};
-    long long t0 = 0;
-#define PROF_MARK(k)                         \
-    if (PROF) {                              \
-        long long now = clock64();           \
-        pc[k] += now - t0;                   \
-        t0 = now;                            \
-    }
     // `groups` (<= kBrGroups) ciphertexts per CTA, first ciphertext of the launch = ct_base; `count` is the
     // exclusive upper bound.  The launcher uses groups < kBrGroups to balance the last wave.
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -671,15 +562,13 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
 
     // Twiddles struct view for the shared phase functions that still take t1
     Twiddles tw;
-    if (XCH) load_twiddles_x(tw, twtab, t);
-    else load_twiddles(tw, twtab, t);
+    load_twiddles_x(tw, twtab, t);
 
     int tile = 0;
 #pragma unroll 1
     for (int i = 0; i < kLweN; i++) {
         const int d = rot[i];
         const bool skip = (d == 0);
-        if (PROF) t0 = clock64();
         cplx out[3][8];
 #pragma unroll
         for (int c = 0; c < 3; c++)
@@ -718,27 +607,18 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                     v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
                                 digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
                 }
-                PROF_MARK(0);  // build
                 cplx *s = flip ? scr1 : scr0;
                 flip ^= 1;
                 fwd_p1(v, s, tw, t);
                 group_sync(bar);
-                if (XCH) {
-                    fwd_p2x(v, s, tw, t);
-                    exchange8<-1>(v, t & 7);
-                } else {
-                    fwd_p2(v, s, tw, t);
-                    group_sync(bar);
-                }
+                fwd_p2x(v, s, tw, t);
+                exchange8<-1>(v, t & 7);
                 const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
-                PROF_MARK(1);  // forward passes 1-2
                 mbar_wait(full + buf, use & 1);  // requested a whole FFT ago: normally already complete
-                PROF_MARK(2);  // tile wait
                 cplx kc[8], kn[8];
 #pragma unroll
                 for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];  // column 0, overlaps the last pass
-                if (XCH) fwd_p3x(v);
-                else fwd_p3(v, s, t);
+                fwd_p3x(v);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     if (c < 2) {
@@ -750,7 +630,6 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
 #pragma unroll
                     for (int k3 = 0; k3 < 8; k3++) kc[k3] = kn[k3];
                 }
-                PROF_MARK(3);  // pass 3 + multiply-accumulate
             } else {
                 mbar_wait(full + buf, use & 1);
             }
@@ -761,18 +640,11 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
         for (int c = 0; c < 3; c++) {
             cplx *s = flip ? scr1 : scr0;
             flip ^= 1;
-            if (XCH) {
-                inv_p3x(out[c]);
-                exchange8<1>(out[c], t & 7);
-                inv_p2x(out[c], s, tw, t);
-            } else {
-                inv_p3(out[c], s, t);
-                group_sync(bar);
-                inv_p2(out[c], s, tw, t);
-            }
+            inv_p3x(out[c]);
+            exchange8<1>(out[c], t & 7);
+            inv_p2x(out[c], s, tw, t);
             group_sync(bar);
             inv_p1(out[c], s, tw, t);
-            PROF_MARK(4);  // inverse transform
             u64x2 *p = acc + c * 512;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
@@ -781,12 +653,8 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
                 w.hi += torus_from_scaled(out[c][m].y);
                 p[t + 64 * m] = w;
             }
-            PROF_MARK(5);  // torus rounding + accumulator update
         }
     }
-    if (PROF && prof && blockIdx.x == 0 && threadIdx.x == 0)
-        for (int k = 0; k < 6; k++) prof[k] = (unsigned long long)pc[k];
-#undef PROF_MARK
     group_sync(bar);
     uint64_t *o = acc_out + (size_t)ct * kGlweWords;
     for (int w = t; w < 3 * 512; w += 64) {
@@ -808,8 +676,21 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
 //     occupancy): 13.7 ms, 136 B of spills;
 //   * pass-2 twiddles in a shared table: 13.3 ms; balancing the last wave with 3-group CTAs: -2 % only,
 //     because a group's step is a latency chain that does not speed up when its neighbours leave.
-// Per-step cycle budget of a v3 group (CBS_BR_PROF=1): build 4.2 k, forward passes 3.3 k, pass 3 + MAC 2.8 k,
+// Per-step cycle budget of a v3 group (clock64 probes, round 1): build 4.2 k, forward passes 3.3 k, pass 3 + MAC 2.8 k,
 // inverse 4.2 k, torus + update 1.5 k, tile wait 0.5 k.
+// Round 2, all parity-green on B200 and all slower (code in git history, commit 1d4... "Blind rotation experiments";
+// numbers in profiles/r02_brbench_variants.txt, ncu summaries profiles/r02_br_*_ncu.txt):
+//   * twiddles in TENSOR MEMORY (tcgen05.ld/st, SASS LDTM/STTM; tools/bench_tmem.cu: 360-470 B/clk/SM next to an
+//     unaffected shared-memory pipe) so that 5 or 6 groups fit the 168-register cap of a 320/384-thread CTA, one
+//     transpose tile per group and a ring of single-polynomial tiles: 10.3 ms per wave of 888 (6 groups) against
+//     5.8 ms per wave of 592 - the ring is one BSK row deep at 6 groups (227 KB of shared memory), so every group
+//     waits for the slowest one three times per step (15 % of all samples on the tile wait);
+//   * a one-warp 512-point transform (16 points per thread, shuffles only, tables in tensor memory) with a TEAM of
+//     three warps per ciphertext exchanging spectra through tensor memory: shared-memory pipe 58 -> 47 %, no transpose
+//     tiles, 5-row ring - but the three warps of a team share a scheduler (tensor-memory lane quarter = warp % 4 =
+//     scheduler) and run in lock step: 6.7 ms per 592;
+//   * the same transform with one warp per ciphertext (8 free-running warps per SM, output columns accumulated through
+//     tensor memory): 130 KB of code (stall_no_instruction 0.77 per issue) and a 4-tile ring: 18.1 ms per 1184.
 
 // ---- low-latency blind rotation for small batches -------------------------------------------------------------
 // k_blind_rotate_v3 keeps one ciphertext per 64-thread group, so a step is a serial chain of 3 builds, 6 transforms and
@@ -975,958 +856,43 @@ __global__ void __launch_bounds__(kLlTeamThreads * kLlTeams, 1) k_blind_rotate_l
     }
 }
 
-// ---- v5: twiddles in tensor memory, 5 or 6 groups per SM ------------------------------------------------------
-// ncu r01b (profiles/r01b_blind_rotate_ncu_full.csv): v3 is a latency chain at 8 warps per SM (FP64 pipe 46 %, shared
-// pipe 58 %, issue slots 52 % of peak: three co-limiting pipes, none saturated), pinned there by 246 registers per
-// thread, 64 of which hold the per-thread pass-1/pass-2 twiddles.  Blackwell's tensor memory (256 KB per SM, idle in an
-// FP64 kernel) is addressable per lane with tcgen05.ld/st (SASS LDTM/STTM), so it serves as a second, thread-private
-// register file: every thread parks its 16 complex twiddles (64 words) there once and fetches them 4 at a time right
-// before the multiply.  With the key prefetch double buffer gone too, a group fits the 168-register cap of a 384-thread
-// CTA, and with ONE transpose tile per group (a second named barrier orders its reuse) and a ring of single-polynomial
-// key tiles, G = 6 groups (12 warps, 3 per scheduler) fit the 227 KB of shared memory.
-//   shared memory: G x (24 KB accumulator + 8 KB tile) + R x 8 KB ring + G x 1.5 KB rotations + barriers
-constexpr int kTwTmemWords = 64;  // per thread: t1x[8], t2x[8] as (re, im) doubles
-template <int G>
-struct Br5 {
-    static constexpr int kRing = (G >= 6) ? 3 : 6;            // key tiles of ONE Fourier polynomial (8 KB)
-    static constexpr int kPolyBytes = 512 * 16;
-    static constexpr int kGroupSmem = kGlweWords * 8 + kPolyBytes;  // 32 KB
-    static constexpr int kRingOff = G * kGroupSmem;
-    static constexpr int kBarOff = kRingOff + kRing * kPolyBytes;
-    static constexpr int kRotOff = kBarOff + 2 * kRing * 8 + 16;   // + tmem slot
-    static constexpr int kSmemBytes = kRotOff + G * kLweN * 2;
-};
-
-__device__ __forceinline__ void tmem_alloc_cols(uint32_t *slot, int cols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_cols(uint32_t addr, int cols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// four complex doubles (16 words) of this thread's TMEM row, columns [col, col + 16)
-__device__ __forceinline__ void tmem_ld_c4_issue(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-// the wait carries the destination registers as in/out operands so no use can be scheduled above it
-__device__ __forceinline__ void tmem_ld_c4_wait(uint32_t (&r)[16])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
-}
-__device__ __forceinline__ cplx tw_of(const uint32_t (&r)[16], int k)
-{
-    return cplx{__hiloint2double((int)r[4 * k + 1], (int)r[4 * k]), __hiloint2double((int)r[4 * k + 3], (int)r[4 * k + 2])};
-}
-__device__ __forceinline__ void tmem_st_c4(uint32_t taddr, const cplx *w)
-{
-    uint32_t r[16];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        r[4 * k] = (uint32_t)__double2loint(w[k].x);
-        r[4 * k + 1] = (uint32_t)__double2hiint(w[k].x);
-        r[4 * k + 2] = (uint32_t)__double2loint(w[k].y);
-        r[4 * k + 3] = (uint32_t)__double2hiint(w[k].y);
-    }
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-
-// transform phases of fft512.cuh ("x" variant) with the per-thread twiddles fetched from TMEM: tm = this warp's TMEM
-// address (lane quarter + column base); columns [0, 32) = t1x[0..7], [32, 64) = t2x[0..7]
-__device__ __forceinline__ void fwd_p1_tm(cplx v[8], cplx *scr, uint32_t tm, int t)
-{
-    const double cr[8] = CBS_CM_RE, ci[8] = CBS_CM_IM;
-    uint32_t wa[16], wb[16];
-    tmem_ld_c4_issue(tm, wa);
-#pragma unroll
-    for (int m = 1; m < 8; m++) v[m] = cmul(v[m], cplx{cr[m], ci[m]});
-    dft8<false>(v);
-    const int a = t & 7, b = t >> 3;
-    tmem_ld_c4_wait(wa);
-    tmem_ld_c4_issue(tm + 16, wb);
-#pragma unroll
-    for (int k1 = 0; k1 < 4; k1++) scr[slot(k1, a, b)] = cmul(v[k1], tw_of(wa, k1));
-    tmem_ld_c4_wait(wb);
-#pragma unroll
-    for (int k1 = 4; k1 < 8; k1++) scr[slot(k1, a, b)] = cmul(v[k1], tw_of(wb, k1 - 4));
-}
-__device__ __forceinline__ void fwd_p2x_tm(cplx v[8], const cplx *scr, uint32_t tm, int t)
-{
-    const int k1 = t >> 3, tp = t & 7;
-    uint32_t wa[16], wb[16];
-    tmem_ld_c4_issue(tm + 32, wa);
-#pragma unroll
-    for (int mp = 0; mp < 8; mp++) v[mp] = scr[slot(k1, tp, mp)];
-    dft8<false>(v);
-    tmem_ld_c4_wait(wa);
-    tmem_ld_c4_issue(tm + 48, wb);
-#pragma unroll
-    for (int r = 0; r < 4; r++) v[r] = cmul(v[r], tw_of(wa, r));
-    tmem_ld_c4_wait(wb);
-#pragma unroll
-    for (int r = 4; r < 8; r++) v[r] = cmul(v[r], tw_of(wb, r - 4));
-}
-__device__ __forceinline__ void inv_p2x_tm(cplx v[8], cplx *scr, uint32_t tm, int t)
-{
-    const int k1 = t >> 3, tp = t & 7;
-    uint32_t wa[16], wb[16];
-    tmem_ld_c4_issue(tm + 32, wa);
-    tmem_ld_c4_wait(wa);
-    tmem_ld_c4_issue(tm + 48, wb);
-#pragma unroll
-    for (int r = 0; r < 4; r++) v[r] = cmul_conj(v[r], tw_of(wa, r));
-    tmem_ld_c4_wait(wb);
-#pragma unroll
-    for (int r = 4; r < 8; r++) v[r] = cmul_conj(v[r], tw_of(wb, r - 4));
-    dft8<true>(v);
-#pragma unroll
-    for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
-}
-__device__ __forceinline__ void inv_p1_tm(cplx v[8], const cplx *scr, uint32_t tm, int t)
-{
-    const double cr[8] = CBS_CM_RE, ci[8] = CBS_CM_IM;
-    const int a = t & 7, b = t >> 3;
-    uint32_t wa[16], wb[16];
-    tmem_ld_c4_issue(tm, wa);
-    tmem_ld_c4_wait(wa);
-    tmem_ld_c4_issue(tm + 16, wb);
-#pragma unroll
-    for (int k1 = 0; k1 < 4; k1++) v[k1] = cmul_conj(scr[slot(k1, a, b)], tw_of(wa, k1));
-    tmem_ld_c4_wait(wb);
-#pragma unroll
-    for (int k1 = 4; k1 < 8; k1++) v[k1] = cmul_conj(scr[slot(k1, a, b)], tw_of(wb, k1 - 4));
-    dft8<true>(v);
-#pragma unroll
-    for (int m = 1; m < 8; m++) v[m] = cmul_conj(v[m], cplx{cr[m], ci[m]});
-}
-
-template <int G>
-__global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v5(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out,
-                                                                int count, const double *__restrict__ bsk_f,
-                                                                const double *__restrict__ twtab)
-{
-    using L = Br5<G>;
-    constexpr int R = L::kRing;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ct = blockIdx.x * G + gi;
-    unsigned char *ring = smem_raw + L::kRingOff;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L::kBarOff);
-    uint64_t *empty = full + R;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + R);
-    const int active_groups = min(G, count - blockIdx.x * G);
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < R; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, 2 * active_groups);  // one arrive per WARP (32 same-address arrives serialise in the LSU)
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tmem_alloc_cols(tmem_slot, 256);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // warp w reaches TMEM lanes 32 * (w % 4) .. + 31 only; the (up to three) warps of a lane quarter take 64 columns each
-    const uint32_t tm = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(kTwTmemWords * (warp >> 2));
-    const int t = threadIdx.x & 63;
-    {
-        Twiddles tw;
-        load_twiddles_x(tw, twtab, t);
-        tmem_st_c4(tm, tw.t1);
-        tmem_st_c4(tm + 16, tw.t1 + 4);
-        tmem_st_c4(tm + 32, tw.t2);
-        tmem_st_c4(tm + 48, tw.t2 + 4);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    if (ct < count) {
-        const bool producer = (threadIdx.x == 0);
-        const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
-        constexpr int kTiles = kLweN * 9;
-        if (producer)
-            for (int b = 0; b < R; b++)
-                tma_load_tile(ring + b * L::kPolyBytes, bsk_bytes + (size_t)b * L::kPolyBytes, L::kPolyBytes, full + b);
-        __syncwarp();
-
-        unsigned char *base = smem_raw + (size_t)gi * L::kGroupSmem;
-        u64x2 *acc = reinterpret_cast<u64x2 *>(base);  // [3][512] pairs (coef j, coef j + 512)
-        cplx *scr = reinterpret_cast<cplx *>(base + kGlweWords * 8);
-        const int bar_raw = 1 + gi, bar_war = 1 + G + gi;  // G <= 7: ids 1 .. 2G <= 14
-        const uint64_t *a = lwe + (size_t)ct * kLweSmall;
-        uint16_t *rot = reinterpret_cast<uint16_t *>(smem_raw + L::kRotOff) + gi * kLweN;
-        for (int q = t; q < kLweN; q += 64) rot[q] = (uint16_t)(modswitch_dev(a[q]) & 2047);
-        {
-            const int bt = modswitch_dev(a[kLweN]);
-            for (int jj = t; jj < 512; jj += 64) {
-                acc[jj] = u64x2{0, 0};
-                acc[512 + jj] = u64x2{0, 0};
-                u64x2 b;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int j = jj + 512 * h;
-                    const int e = (j + bt) & 2047;
-                    const int i = e & 1023;
-                    uint64_t val = 1ull << (61 - 2 * (i & 7));
-                    const bool neg = (i < 512) != ((e & 1024) != 0);
-                    (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
-                }
-                acc[1024 + jj] = b;
-            }
-        }
-        group_sync(bar_raw);
-
-        int tile = 0;  // next key tile this thread consumes (same sequence in every thread)
-        // Producer (thread 0): tiles are requested in consumption order; tile q reuses the slot of tile q - R, so it can be
-        // requested once every group has released that one.  pump(0) takes whatever is free without blocking (called at
-        // several points of a row so that a request is never late); pump(n) blocks until tiles < n are requested (called
-        // right before this thread consumes them itself).  A dedicated producer warp would be the 13th warp of the
-        // CTA, and registers are allocated in units of 4 warps: it would cost every thread 40 registers.
-        int next_fill = R;
-        auto pump = [&](int need_upto) {
-            while (next_fill < kTiles) {
-                const int sl = next_fill % R, prev_use = next_fill / R - 1;
-                if (next_fill < need_upto) mbar_wait(empty + sl, prev_use & 1);
-                else if (!mbar_test(empty + sl, prev_use & 1)) break;
-                tma_load_tile(ring + sl * L::kPolyBytes, bsk_bytes + (size_t)next_fill * L::kPolyBytes, L::kPolyBytes, full + sl);
-                next_fill++;
-            }
-        };
-#pragma unroll 1
-        for (int i = 0; i < kLweN; i++) {
-            const int d = rot[i];
-            const bool skip = (d == 0);
-            cplx out[3][8];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
-#pragma unroll 1
-            for (int r = 0; r < 3; r++) {
-                if (producer) pump(0);
-                __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-                if (!skip) {
-                    cplx v[8];
-                    const u64x2 *p = acc + r * 512;
-#pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        const int jj = t + 64 * m;
-                        const int e0 = (jj - d) & 2047;
-                        const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];
-                        const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
-                        const bool sw = (e0 & 512) != 0;
-                        const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
-                        const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
-                        const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
-                        const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
-                        v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
-                                    digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
-                    }
-                    group_sync(bar_war);  // the partner warp has finished reading the tile of the previous transform
-                    fwd_p1_tm(v, scr, tm, t);
-                    group_sync(bar_raw);
-                    if (producer) pump(0);
-                    __syncwarp();
-                    fwd_p2x_tm(v, scr, tm, t);
-                    exchange8<-1>(v, t & 7);
-                    fwd_p3x(v);
-                    if (producer) pump(tile + 3);
-                    __syncwarp();
-#pragma unroll
-                    for (int c = 0; c < 3; c++, tile++) {
-                        const int buf = tile % R;
-                        mbar_wait(full + buf, (tile / R) & 1);
-                        const cplx *key = reinterpret_cast<const cplx *>(ring + buf * L::kPolyBytes) + t;
-#pragma unroll
-                        for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[k3 * 64]);
-                        __syncwarp();  // every lane's tile reads have been consumed by the products above
-                        if (lane == 0) mbar_arrive(empty + buf);
-                    }
-                } else {
-                    if (producer) pump(tile + 3);
-                    __syncwarp();
-#pragma unroll
-                    for (int c = 0; c < 3; c++, tile++) {
-                        const int buf = tile % R;
-                        mbar_wait(full + buf, (tile / R) & 1);
-                        if (lane == 0) mbar_arrive(empty + buf);
-                    }
-                }
-            }
-            if (skip) continue;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                inv_p3x(out[c]);
-                exchange8<1>(out[c], t & 7);
-                if (producer) pump(0);
-                __syncwarp();
-                group_sync(bar_war);
-                inv_p2x_tm(out[c], scr, tm, t);
-                group_sync(bar_raw);
-                inv_p1_tm(out[c], scr, tm, t);
-                u64x2 *p = acc + c * 512;
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    u64x2 w = p[t + 64 * m];
-                    w.lo += torus_from_scaled(out[c][m].x);
-                    w.hi += torus_from_scaled(out[c][m].y);
-                    p[t + 64 * m] = w;
-                }
-            }
-        }
-        group_sync(bar_raw);
-        uint64_t *o = acc_out + (size_t)ct * kGlweWords;
-        for (int w = t; w < 3 * 512; w += 64) {
-            const u64x2 x = acc[w];
-            const int c = w >> 9, jj = w & 511;
-            o[c * 1024 + jj] = x.lo;
-            o[c * 1024 + jj + 512] = x.hi;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 256);
-}
-
-// ---- W: one warp per polynomial, one team of three warps per ciphertext -------------------------------------------------
-// (design notes in fftw512.cuh)  A CTA holds 4 ciphertexts.  Team q = warps q, q + 4, q + 8: they share lane quarter q
-// of tensor memory and scheduler q.  Warp r of a team owns accumulator polynomial r: it builds the digits of polynomial r
-// (16 points per thread), transforms them with shuffles only, parks the spectrum in TENSOR MEMORY where its two team
-// mates read it (same lane, other warp: the one exchange pattern tcgen05.ld/st offers across warps), accumulates output
-// column r against the three BSK row tiles of the step, inverse-transforms and updates polynomial r - which no other
-// warp ever touches, so the accumulator needs no cross-warp synchronisation at all.  Per step a team executes two 96-thread
-// barriers (spectra published / spectra consumed) where k_blind_rotate_v3 executes six 64-thread barriers per group
-// plus the lock-step of 12 transposes through shared memory.  Shared memory holds only the accumulators (24 KB per
-// ciphertext) and a FIVE-row ring of BSK tiles; the per-lane transform tables (160 words) sit in tensor memory.
-constexpr int kWTeams = 4;
-constexpr int kWRing = 5;                                     // ring depth in BSK rows (24,576 B each)
-constexpr int kWRingOff = kWTeams * kGlweWords * 8;           // 98,304
-constexpr int kWBarOff = kWRingOff + kWRing * kBrTileBytes;   // 221,184
-constexpr int kWRotOff = kWBarOff + 2 * kWRing * 8 + 16;
-constexpr int kWSmemBytes = kWRotOff + kWTeams * kLweN * 2;   // 227,424
-constexpr int kWSpecCol = 4 * kWTabCplx;                      // tensor-memory columns: tables [0, 160), spectra 160 + 64 r
-
-// four complex doubles <-> 16 tensor-memory columns of this thread's lane.  The 32-bit halves are packed / unpacked INSIDE the
-// asm block (mov.b64), where ptxas coalesces them with the 64-bit registers: formed with __hiloint2double outside, every
-// double cost an IMAD.MOV (ncu r02_br_w1: 9 % of all instructions were such moves).
-__device__ __forceinline__ void tmem_ld_c4(uint32_t taddr, cplx *w)
-{
-    asm volatile(
-        "{\n\t.reg .b32 t<16>;\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%8];\n\t"
-        "tcgen05.wait::ld.sync.aligned;\n\t"
-        "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t"
-        "mov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t}"
-        : "=d"(w[0].x), "=d"(w[0].y), "=d"(w[1].x), "=d"(w[1].y), "=d"(w[2].x), "=d"(w[2].y), "=d"(w[3].x), "=d"(w[3].y)
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_c4d(uint32_t taddr, const cplx *w)
-{
-    asm volatile(
-        "{\n\t.reg .b32 t<16>;\n\t"
-        "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\t"
-        "mov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\t"
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15};\n\t}" ::"r"(taddr),
-        "d"(w[0].x), "d"(w[0].y), "d"(w[1].x), "d"(w[1].y), "d"(w[2].x), "d"(w[2].y), "d"(w[3].x), "d"(w[3].y)
-        : "memory");
-}
-struct TmemTab {
-    uint32_t base;
-    __device__ __forceinline__ void get4(int first, cplx *w) const { tmem_ld_c4(base + 4 * first, w); }
-};
-struct GlobalTab {
-    const double *p;
-    __device__ __forceinline__ void get4(int first, cplx *w) const
-    {
-#pragma unroll
-        for (int k = 0; k < 4; k++) w[k] = ldg_cplx(p + (size_t)(first + k) * 2);
-    }
-};
-
-// standard -> Fourier conversion into the W layout: out[poly][rho][lane] = TRUE bin wbin(lane, rho) / 512
-__global__ void __launch_bounds__(128) k_std_to_fourier_w(const uint64_t *__restrict__ in, double *__restrict__ out, int npoly,
-                                                           const double *__restrict__ wtab)
-{
-    const int lane = threadIdx.x & 31;
-    const int poly = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (poly >= npoly) return;
-    const GlobalTab tab{wtab + (size_t)lane * kWTabCplx * 2};
-    const uint64_t *p = in + (size_t)poly * 1024;
-    cplx v[16];
-#pragma unroll
-    for (int m = 0; m < 16; m++) v[m] = cplx{torus_to_double(p[lane + 32 * m]), torus_to_double(p[lane + 32 * m + 512])};
-    wfwd_s1(v, tab);
-    wexchange_a<-1>(v, lane);
-    wfwd_s2(v, tab);
-    wexchange_b<-1>(v, lane);
-    wfwd_s3(v);
-    double *o = out + (size_t)poly * kFourierPolyDoubles;
-#pragma unroll
-    for (int rho = 0; rho < 16; rho++) {
-        // the transform leaves conj(phi) * X with phi = W4^e = (-i)^e: multiply by phi
-        const int e = wphase_exp(lane, rho);
-        cplx x = v[rho];
-        if (e == 1) x = cplx{v[rho].y, -v[rho].x};
-        else if (e == 2) x = cplx{-v[rho].x, -v[rho].y};
-        else if (e == 3) x = cplx{-v[rho].y, v[rho].x};
-        *reinterpret_cast<double2 *>(o + (size_t)(rho * 32 + lane) * 2) = make_double2(x.x * (1.0 / 512.0), x.y * (1.0 / 512.0));
-    }
-}
-
-void launch_std_to_fourier_w(const uint64_t *in, double *out, int npoly, const double *wtab, cudaStream_t s)
-{
-    if (npoly <= 0) return;
-    k_std_to_fourier_w<<<(npoly + 3) / 4, 128, 0, s>>>(in, out, npoly, wtab);
-}
-
-__global__ void __launch_bounds__(96 * kWTeams, 1) k_blind_rotate_w(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out,
-                                                                     int count, const double *__restrict__ bsk_w,
-                                                                     const double *__restrict__ wtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, r = warp >> 2;  // team (lane quarter), polynomial / output column of this warp
-    const int ct = blockIdx.x * kWTeams + q;
-    unsigned char *ring = smem_raw + kWRingOff;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kWBarOff);
-    uint64_t *empty = full + kWRing;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + kWRing);
-    const int active_teams = min(kWTeams, count - blockIdx.x * kWTeams);
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < kWRing; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, 3 * active_teams);  // one arrive per warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tmem_alloc_cols(tmem_slot, 512);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tq = *tmem_slot + ((uint32_t)(32 * q) << 16);  // lane quarter q, column 0
-    if (r == 0) {  // the tables depend on the lane only: one copy per lane quarter, shared by the three warps of the team
-        const double *src = wtab + (size_t)lane * kWTabCplx * 2;
-        for (int e = 0; e < kWTabCplx; e += 4) {
-            cplx w[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) w[k] = ldg_cplx(src + (size_t)(e + k) * 2);
-            tmem_st_c4(tq + 4 * e, w);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (ct < count) {
-        const TmemTab tab{tq};
-        const bool producer = (threadIdx.x == 0);
-        const char *bsk_bytes = reinterpret_cast<const char *>(bsk_w);
-        constexpr int kTiles = kLweN * 3;
-        if (producer)
-            for (int b = 0; b < kWRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
-        __syncwarp();
-        u64x2 *p = reinterpret_cast<u64x2 *>(smem_raw + (size_t)q * kGlweWords * 8) + r * 512;  // polynomial r as pairs (j, j + 512)
-        const int tbar = 1 + q;
-        const uint64_t *a = lwe + (size_t)ct * kLweSmall;
-        uint16_t *rot = reinterpret_cast<uint16_t *>(smem_raw + kWRotOff) + q * kLweN;
-        for (int i = lane + 32 * r; i < kLweN; i += 96) rot[i] = (uint16_t)(modswitch_dev(a[i]) & 2047);
-        {
-            const int bt = modswitch_dev(a[kLweN]);
-            for (int jj = lane; jj < 512; jj += 32) {
-                u64x2 b{0, 0};
-                if (r == 2) {
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int j = jj + 512 * h;
-                        const int e = (j + bt) & 2047;
-                        const int i = e & 1023;
-                        uint64_t val = 1ull << (61 - 2 * (i & 7));
-                        const bool neg = (i < 512) != ((e & 1024) != 0);
-                        (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
-                    }
-                }
-                p[jj] = b;
-            }
-        }
-        named_sync(tbar, 96);
-
-        int next_fill = kWRing;
-        auto pump = [&](int need_upto) {
-            while (next_fill < kTiles) {
-                const int sl = next_fill % kWRing, prev_use = next_fill / kWRing - 1;
-                if (next_fill < need_upto) mbar_wait(empty + sl, prev_use & 1);
-                else if (!mbar_test(empty + sl, prev_use & 1)) break;
-                tma_load_tile(ring + sl * kBrTileBytes, bsk_bytes + (size_t)next_fill * kBrTileBytes, kBrTileBytes, full + sl);
-                next_fill++;
-            }
-        };
-        bool spectra_in_use = false;  // the previous step's spectra may still be read by a team mate
-#pragma unroll 1
-        for (int i = 0; i < kLweN; i++) {
-            const int d = rot[i];
-            const int t0 = 3 * i;
-            if (producer) pump(0);
-            __syncwarp();
-            if (d == 0) {  // trivial rotation: the product is exactly zero (pbs.rs:111); only the ring bookkeeping remains
-                if (producer) pump(t0 + 3);
-                __syncwarp();
-#pragma unroll 1
-                for (int rr = 0; rr < 3; rr++) {
-                    const int tile = t0 + rr;
-                    mbar_wait(full + tile % kWRing, (tile / kWRing) & 1);
-                    if (lane == 0) mbar_arrive(empty + tile % kWRing);
-                }
-                continue;
-            }
-            cplx v[16];
-#pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const int jj = lane + 32 * m;
-                const int e0 = (jj - d) & 2047;
-                const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];
-                const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
-                const bool sw = (e0 & 512) != 0;
-                const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
-                const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
-                const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
-                const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
-                v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
-                            digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
-            }
-            wfwd_s1(v, tab);
-            wexchange_a<-1>(v, lane);
-            wfwd_s2(v, tab);
-            wexchange_b<-1>(v, lane);
-            wfwd_s3(v);
-            if (producer) pump(t0 + 3);
-            __syncwarp();
-            // own product: column r of row r
-            cplx out[16];
-            {
-                const int tile = t0 + r;
-                mbar_wait(full + tile % kWRing, (tile / kWRing) & 1);
-                const cplx *key = reinterpret_cast<const cplx *>(ring + (tile % kWRing) * kBrTileBytes) + r * 512 + lane;
-#pragma unroll
-                for (int k = 0; k < 16; k++) out[k] = cmul(v[k], key[k * 32]);
-            }
-            // publish the spectrum in tensor memory
-            if (spectra_in_use) named_sync(tbar, 96);  // every team mate has finished reading the previous step's spectra
-#pragma unroll
-            for (int c4 = 0; c4 < 4; c4++) tmem_st_c4d(tq + kWSpecCol + 64 * r + 16 * c4, v + 4 * c4);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            named_sync(tbar, 96);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            spectra_in_use = true;
-#pragma unroll
-            for (int s = 1; s < 3; s++) {
-                const int rr = (r + s) % 3;
-                const int tile = t0 + rr;
-                mbar_wait(full + tile % kWRing, (tile / kWRing) & 1);
-                const cplx *key = reinterpret_cast<const cplx *>(ring + (tile % kWRing) * kBrTileBytes) + r * 512 + lane;
-                const TmemTab spec{tq + kWSpecCol + 64 * rr};
-#pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) {
-                    cplx w[4];
-                    spec.get4(4 * c4, w);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) cfma(out[4 * c4 + k], w[k], key[(4 * c4 + k) * 32]);
-                }
-            }
-            __syncwarp();  // every lane's tile reads have been consumed by the products above
-            if (lane == 0) {
-#pragma unroll
-                for (int rr = 0; rr < 3; rr++) mbar_arrive(empty + (t0 + rr) % kWRing);
-            }
-            winv_s3(out);
-            wexchange_b<1>(out, lane);
-            winv_s2(out, tab);
-            wexchange_a<1>(out, lane);
-            winv_s1(out, tab);
-#pragma unroll
-            for (int m = 0; m < 16; m++) {
-                u64x2 w = p[lane + 32 * m];
-                w.lo += torus_from_scaled(out[m].x);
-                w.hi += torus_from_scaled(out[m].y);
-                p[lane + 32 * m] = w;
-            }
-            __syncwarp();  // polynomial r is complete before this warp's next rotated reads
-        }
-        uint64_t *o = acc_out + (size_t)ct * kGlweWords + r * 1024;
-        for (int w = lane; w < 512; w += 32) {
-            const u64x2 x = p[w];
-            o[w] = x.lo;
-            o[w + 512] = x.hi;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 512);
-}
-
-// ---- W1: one warp per CIPHERTEXT, eight free-running warps per SM ---------------------------------------------------------
-// ncu on k_blind_rotate_w (profiles/r02_br_w1_ncu.csv): the three warps of a team share a scheduler and run in lock step
-// (two team barriers per step), so their FP64-heavy phases collide (math_pipe_throttle 1.1 per issue) and their integer
-// phases leave the FP64 pipe idle: 47 % FP64 utilisation, no better than k_blind_rotate_v3.  Here a warp owns a whole
-// ciphertext: no barrier of any kind, no cross-warp data, the eight warps of a CTA drift freely and interleave their
-// integer and FP64 phases on each scheduler.  What made one-warp-per-ciphertext impossible before is the register file:
-// three output columns of 16 complex points are 192 registers.  Column 0 stays in registers; columns 1 and 2 are
-// accumulated through TENSOR MEMORY (read-modify-write of 4 complex values at a time), which also holds the per-lane
-// transform tables.  Shared memory: 8 accumulators (192 KB) and a ring of four single-polynomial BSK tiles.
-constexpr int kW1Warps = 8;
-constexpr int kW1Ring = 4;
-constexpr int kW1PolyBytes = 512 * 16;
-constexpr int kW1RingOff = kW1Warps * kGlweWords * 8;                  // 196,608
-constexpr int kW1BarOff = kW1RingOff + kW1Ring * kW1PolyBytes;         // 229,376
-constexpr int kW1SmemBytes = kW1BarOff + 2 * kW1Ring * 8 + 16;         // 229,456
-constexpr int kW1OutCol = 4 * kWTabCplx;                               // tensor-memory columns 160 + 128 h: columns 1, 2 of warp h
-
-__global__ void __launch_bounds__(32 * kW1Warps, 1) k_blind_rotate_w1(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out,
-                                                                       int count, const double *__restrict__ bsk_w,
-                                                                       const double *__restrict__ wtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, h = warp >> 2;
-    const int ct = blockIdx.x * kW1Warps + warp;
-    unsigned char *ring = smem_raw + kW1RingOff;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kW1BarOff);
-    uint64_t *empty = full + kW1Ring;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + kW1Ring);
-    const int active_warps = min(kW1Warps, count - blockIdx.x * kW1Warps);
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < kW1Ring; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, active_warps);  // one arrive per warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tmem_alloc_cols(tmem_slot, 512);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tq = *tmem_slot + ((uint32_t)(32 * q) << 16);
-    if (h == 0) {  // one copy of the per-lane tables per lane quarter
-        const double *src = wtab + (size_t)lane * kWTabCplx * 2;
-        for (int e = 0; e < kWTabCplx; e += 4) {
-            cplx w[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) w[k] = ldg_cplx(src + (size_t)(e + k) * 2);
-            tmem_st_c4d(tq + 4 * e, w);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (ct < count) {
-        const TmemTab tab{tq};
-        const uint32_t tout = tq + kW1OutCol + 128 * h;  // column c (1 or 2) at tout + 64 (c - 1)
-        const bool producer = (threadIdx.x == 0);
-        const char *bsk_bytes = reinterpret_cast<const char *>(bsk_w);
-        constexpr int kTiles = kLweN * 9;
-        if (producer)
-            for (int b = 0; b < kW1Ring; b++) tma_load_tile(ring + b * kW1PolyBytes, bsk_bytes + (size_t)b * kW1PolyBytes, kW1PolyBytes, full + b);
-        __syncwarp();
-        u64x2 *acc = reinterpret_cast<u64x2 *>(smem_raw + (size_t)warp * kGlweWords * 8);  // [3][512] pairs (j, j + 512)
-        const uint64_t *a = lwe + (size_t)ct * kLweSmall;
-        {
-            const int bt = modswitch_dev(a[kLweN]);
-            for (int jj = lane; jj < 512; jj += 32) {
-                u64x2 b;
-#pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const int j = jj + 512 * hh;
-                    const int e = (j + bt) & 2047;
-                    const int i = e & 1023;
-                    uint64_t val = 1ull << (61 - 2 * (i & 7));
-                    const bool neg = (i < 512) != ((e & 1024) != 0);
-                    (hh ? b.hi : b.lo) = neg ? (0ull - val) : val;
-                }
-                acc[jj] = u64x2{0, 0};
-                acc[512 + jj] = u64x2{0, 0};
-                acc[1024 + jj] = b;
-            }
-        }
-        __syncwarp();
-        int next_fill = kW1Ring;
-        auto pump = [&](int need_upto) {
-            while (next_fill < kTiles) {
-                const int sl = next_fill % kW1Ring, prev_use = next_fill / kW1Ring - 1;
-                if (next_fill < need_upto) mbar_wait(empty + sl, prev_use & 1);
-                else if (!mbar_test(empty + sl, prev_use & 1)) break;
-                tma_load_tile(ring + sl * kW1PolyBytes, bsk_bytes + (size_t)next_fill * kW1PolyBytes, kW1PolyBytes, full + sl);
-                next_fill++;
-            }
-        };
-        uint64_t a_next = __ldg(a);  // mask word of the next step, fetched one step ahead
-        int tile = 0;
-#pragma unroll 1
-        for (int i = 0; i < kLweN; i++) {
-            const int d = modswitch_dev(a_next) & 2047;
-            a_next = __ldg(a + min(i + 1, kLweN - 1));
-            if (d == 0) {  // trivial rotation: the external product is exactly zero (pbs.rs:111); ring bookkeeping only
-#pragma unroll 1
-                for (int k = 0; k < 9; k++, tile++) {
-                    if (producer) pump(tile + 1);
-                    __syncwarp();
-                    mbar_wait(full + tile % kW1Ring, (tile / kW1Ring) & 1);
-                    if (lane == 0) mbar_arrive(empty + tile % kW1Ring);
-                }
-                continue;
-            }
-            cplx out0[16];
-#pragma unroll 1
-            for (int r = 0; r < 3; r++) {
-                if (producer) pump(0);
-                __syncwarp();
-                cplx v[16];
-                const u64x2 *p = acc + r * 512;
-#pragma unroll
-                for (int m = 0; m < 16; m++) {
-                    const int jj = lane + 32 * m;
-                    const int e0 = (jj - d) & 2047;
-                    const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];
-                    const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
-                    const bool sw = (e0 & 512) != 0;
-                    const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
-                    const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
-                    const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
-                    const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
-                    v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
-                                digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
-                }
-                wfwd_s1(v, tab);
-                wexchange_a<-1>(v, lane);
-                if (producer) pump(0);
-                __syncwarp();
-                wfwd_s2(v, tab);
-                wexchange_b<-1>(v, lane);
-                wfwd_s3(v);
-                // column 0: registers
-                {
-                    if (producer) pump(tile + 1);
-                    __syncwarp();
-                    mbar_wait(full + tile % kW1Ring, (tile / kW1Ring) & 1);
-                    const cplx *key = reinterpret_cast<const cplx *>(ring + (tile % kW1Ring) * kW1PolyBytes) + lane;
-                    if (r == 0) {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) out0[k] = cmul(v[k], key[k * 32]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) cfma(out0[k], v[k], key[k * 32]);
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty + tile % kW1Ring);
-                    tile++;
-                }
-                // columns 1 and 2: accumulated through tensor memory, four complex values at a time
-#pragma unroll
-                for (int c = 1; c < 3; c++, tile++) {
-                    if (producer) pump(tile + 1);
-                    __syncwarp();
-                    mbar_wait(full + tile % kW1Ring, (tile / kW1Ring) & 1);
-                    const cplx *key = reinterpret_cast<const cplx *>(ring + (tile % kW1Ring) * kW1PolyBytes) + lane;
-                    const uint32_t tc = tout + 64 * (c - 1);
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        cplx w[4];
-                        if (r == 0) {
-#pragma unroll
-                            for (int k = 0; k < 4; k++) w[k] = cmul(v[4 * c4 + k], key[(4 * c4 + k) * 32]);
-                        } else {
-                            tmem_ld_c4(tc + 16 * c4, w);
-#pragma unroll
-                            for (int k = 0; k < 4; k++) cfma(w[k], v[4 * c4 + k], key[(4 * c4 + k) * 32]);
-                        }
-                        tmem_st_c4d(tc + 16 * c4, w);
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty + tile % kW1Ring);
-                }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // before the next row reads the partial sums back
-            }
-#pragma unroll 1
-            for (int c = 0; c < 3; c++) {
-                if (c > 0) {
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) tmem_ld_c4(tout + 64 * (c - 1) + 16 * c4, out0 + 4 * c4);
-                }
-                winv_s3(out0);
-                wexchange_b<1>(out0, lane);
-                if (producer) pump(0);
-                __syncwarp();
-                winv_s2(out0, tab);
-                wexchange_a<1>(out0, lane);
-                winv_s1(out0, tab);
-                u64x2 *p = acc + c * 512;
-#pragma unroll
-                for (int m = 0; m < 16; m++) {
-                    u64x2 w = p[lane + 32 * m];
-                    w.lo += torus_from_scaled(out0[m].x);
-                    w.hi += torus_from_scaled(out0[m].y);
-                    p[lane + 32 * m] = w;
-                }
-            }
-            __syncwarp();  // the accumulator is complete before the next step's rotated reads
-        }
-        uint64_t *o = acc_out + (size_t)ct * kGlweWords;
-        for (int w = lane; w < 3 * 512; w += 32) {
-            const u64x2 x = acc[w];
-            const int c = w >> 9, jj = w & 511;
-            o[c * 1024 + jj] = x.lo;
-            o[c * 1024 + jj + 512] = x.hi;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 512);
-}
-
-static int br_variant()
-{
-    static int v = -1;
-    if (v < 0) {
-        // 0 = keys by coalesced LDG (first version), 2 = TMA ring + shared-memory transposes (v3),
-        // 3 = TMA ring + shuffle-exchange transforms (default); 0/2 are kept for A/B runs
-        const char *e = getenv("CBS_BR_VARIANT");
-        v = e ? atoi(e) : 3;
-    }
-    return v;
-}
-
 void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc, int count, cudaStream_t s)
 {
     if (count <= 0) return;
-    static bool attr_done[64] = {false};
-    int attr_dev = 0;
-    cudaGetDevice(&attr_dev);
-    bool &attr = attr_done[attr_dev & 63];
-    if (!attr) {
-        cudaFuncSetAttribute(k_blind_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrSmemBytes);
+    // per-device state, initialised once per device (the stage executables call this from one host thread per GPU)
+    static std::once_flag once[64];
+    static int sm_count[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    std::call_once(once[dev], [&] {
         cudaFuncSetAttribute(k_blind_rotate_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, kLlSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_w, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_w1, cudaFuncAttributeMaxDynamicSharedMemorySize, kW1SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v5<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<4>::kSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v5<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<5>::kSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v5<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br5<6>::kSmemBytes);
-        attr = true;
-    }
-    const int grid = (count + kBrGroups - 1) / kBrGroups;
-    static int ll_sms[64] = {0};
-    if (!ll_sms[attr_dev & 63]) cudaDeviceGetAttribute(&ll_sms[attr_dev & 63], cudaDevAttrMultiProcessorCount, attr_dev);
-    // small batches (at most kLlTeams ciphertexts per SM): the 192-thread-team kernel, 2.4x shorter per blind rotation
-    static int ll_mode = -1;  // CBS_BR_LOWLAT: 0 = never, 1 = auto (default), 2 = always
-    if (ll_mode < 0) {
+        cudaFuncSetAttribute(k_blind_rotate_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sm_count[dev] = n > 0 ? n : 1;
+    });
+    const int sms = sm_count[dev];
+    // CBS_BR_LOWLAT: 0 = never use the team kernel, 1 = for small batches and small tails (default), 2 = always
+    static const int ll_mode = [] {
         const char *e = getenv("CBS_BR_LOWLAT");
-        ll_mode = e ? atoi(e) : 1;
-    }
+        return e ? atoi(e) : 1;
+    }();
     auto launch_team = [&](const uint64_t *in, uint64_t *out, int n) {
-        const int teams = n <= ll_sms[attr_dev & 63] ? 1 : kLlTeams;
+        const int teams = n <= sms ? 1 : kLlTeams;
         k_blind_rotate_ll<<<(n + teams - 1) / teams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(in, out, n, K.bsk_f, K.tw, teams);
     };
-    if (br_variant() >= 3 && br_variant() != 4 && br_variant() != 7 && br_variant() != 8 && (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * ll_sms[attr_dev & 63]))) {
+    // small batches (at most kLlTeams ciphertexts per SM): the 192-thread-team kernel, 2.4x shorter per blind rotation
+    if (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * sms)) {
         launch_team(lwe, acc, count);
         return;
     }
     // a last partial wave of at most two ciphertexts per SM also goes to the team kernel (3.2 / 2.4 ms instead of 5.8 ms)
-    if (br_variant() == 3 && ll_mode == 1) {
-        const int wave = ll_sms[attr_dev & 63] * kBrGroups, rem = count % wave;
-        if (count > wave && rem > 0 && rem <= kLlTeams * ll_sms[attr_dev & 63]) {
-            const int head = count - rem;
-            k_blind_rotate_v3<false, true><<<head / kBrGroups, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw, kBrGroups, 0, nullptr);
-            launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, rem);
-            return;
-        }
-    }
-    if (br_variant() == 7 && K.bsk_w) {  // W: team of three warps per ciphertext, 4 ciphertexts per SM
-        const int wave = ll_sms[attr_dev & 63] * kWTeams;
-        int head = count;
-        const int rem = count % wave;
-        if (ll_mode == 1 && count > wave && rem > 0 && rem <= ll_sms[attr_dev & 63]) head = count - rem;  // one per SM: team kernel
-        k_blind_rotate_w<<<(head + kWTeams - 1) / kWTeams, 96 * kWTeams, kWSmemBytes, s>>>(lwe, acc, head, K.bsk_w, K.wtab);
-        if (head < count) launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, count - head);
-        return;
-    }
-    if (br_variant() == 8 && K.bsk_w) {  // W1: one warp per ciphertext, 8 per SM
-        const int wave = ll_sms[attr_dev & 63] * kW1Warps;
-        int head = count;
-        const int rem = count % wave;
-        if (ll_mode == 1 && count > wave && rem > 0 && rem <= kLlTeams * ll_sms[attr_dev & 63]) head = count - rem;
-        k_blind_rotate_w1<<<(head + kW1Warps - 1) / kW1Warps, 32 * kW1Warps, kW1SmemBytes, s>>>(lwe, acc, head, K.bsk_w, K.wtab);
-        if (head < count) launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, count - head);
-        return;
-    }
-    if (br_variant() == 4) {  // v5 code at 4 groups per SM (A/B against v3 at equal occupancy)
-        k_blind_rotate_v5<4><<<(count + 3) / 4, 64 * 4, Br5<4>::kSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-        return;
-    }
-    if (br_variant() == 5 || br_variant() == 6) {
-        // v5: twiddles in tensor memory, 5 or 6 groups per SM; a last partial wave of at most two ciphertexts per SM
-        // goes to the team kernel
-        const int G = br_variant(), wave = ll_sms[attr_dev & 63] * G;
-        int head = count;
-        const int rem = count % wave;
-        if (ll_mode == 1 && count > wave && rem > 0 && rem <= kLlTeams * ll_sms[attr_dev & 63]) head = count - rem;
-        if (G == 5)
-            k_blind_rotate_v5<5><<<(head + 4) / 5, 64 * 5, Br5<5>::kSmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw);
-        else
-            k_blind_rotate_v5<6><<<(head + 5) / 6, 64 * 6, Br5<6>::kSmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw);
-        if (head < count) launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, count - head);
-        return;
-    }
-    if (br_variant() == 0)
-        k_blind_rotate<<<grid, 64 * kBrGroups, kBrSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-    else {
-        // CBS_BR_SPLIT is read once (thread-safe function-local static); the SM count is the per-device value above:
-        // the stage executables call this from one host thread per GPU
-        static const int split = [] {
-            const char *e = getenv("CBS_BR_SPLIT");
-            return e ? atoi(e) : 0;
-        }();
-        const int sms = std::max(1, ll_sms[attr_dev & 63]);
-        const int full_wave = sms * kBrGroups;
-        const int rem = count % full_wave;
-        const bool xch = br_variant() >= 3;
-        auto launch = [&](int blocks, int upto, int g, int base) {
-            if (xch) k_blind_rotate_v3<false, true><<<blocks, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, upto, K.bsk_f, K.tw, g, base, nullptr);
-            else k_blind_rotate_v3<false, false><<<blocks, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, upto, K.bsk_f, K.tw, g, base, nullptr);
-        };
-        // last-wave balancing: a remainder that fits sms x 3 (or x 2) groups runs with fewer groups per SM
-        if (split && count > full_wave && rem > 0 && rem <= sms * (kBrGroups - 1)) {
-            const int head = count - rem;
-            const int g = (rem + sms - 1) / sms;  // groups per CTA in the tail launch
-            launch(head / kBrGroups, head, kBrGroups, 0);
-            launch((rem + g - 1) / g, count, g, head);
-        } else if (getenv("CBS_BR_PROF")) {
-            static unsigned long long *d_prof = nullptr;
-            if (!d_prof) cudaMalloc(&d_prof, 6 * sizeof(unsigned long long));
-            if (xch) k_blind_rotate_v3<true, true><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, kBrGroups, 0, d_prof);
-            else k_blind_rotate_v3<true, false><<<grid, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw, kBrGroups, 0, d_prof);
-            unsigned long long h[6];
-            cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, s);
-            cudaStreamSynchronize(s);
-            fprintf(stderr, "[br prof] cycles: build %llu  fwd12 %llu  tilewait %llu  p3+mac %llu  inverse %llu  torus %llu\n", h[0], h[1],
-                    h[2], h[3], h[4], h[5]);
-        } else {
-            launch(grid, count, kBrGroups, 0);
-        }
-    }
+    const int wave = sms * kBrGroups, rem = count % wave;
+    int head = count;
+    if (ll_mode == 1 && count > wave && rem > 0 && rem <= kLlTeams * sms) head = count - rem;
+    k_blind_rotate_v3<<<(head + kBrGroups - 1) / kBrGroups, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw, kBrGroups, 0);
+    if (head < count) launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, count - head);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1967,18 +933,16 @@ void launch_glev_from_acc(const uint64_t *acc, uint64_t *glev, int count, cudaSt
 // keyswitch_glwe_ciphertext with Split(41) two-limb FFT (fourier_glwe_keyswitch.rs:213-342), add].
 __constant__ int c_kappa_inv[10];  // kappa^-1 mod 2048 for kappa = (1024 >> s) + 1
 
-// ---- trace v2: both key limbs in one pass, two cooperating 64-thread sub-groups per GLWE ----------------
+// ---- trace: both key limbs in one pass, two cooperating 64-thread sub-groups per GLWE -------------------
 // The Split(41) keyswitch needs Sum_F F x K_lo and Sum_F F x K_hi over the same six digit spectra F.
 // Holding both accumulator sets in one thread (192 registers) is impossible, so k_trace ran two
-// passes and recomputed the six forward FFTs (18 FFTs per step).  Here sub-group A accumulates the lo
+// passes and recomputed the six forward FFTs (18 FFTs per step; the first version).  Here sub-group A accumulates the lo
 // limb and sub-group B the hi limb; A transforms the digits of mask polynomial 0, B those of mask
 // polynomial 1, and each spectrum is handed to the partner through an 8 KB shared tile written and read
 // in the owner's register-slot order (no transpose, conflict-free).  12 FFTs per step, 8 warps per SM
 // (was 18 FFTs at 6 warps), and the second GLWE copy (`nxt`) is gone: all permuted reads of a step
 // happen before its first write.
 constexpr int kTr2Glwe = 2;                                              // GLWEs per CTA (4 sub-groups, 256 threads)
-constexpr int kTr2GlweSmem = kGlweWords * 8 + 2 * 2 * 8192 + 2 * 2 * 8192;  // cur 24 KB + tiles 32 KB + exchange 32 KB
-constexpr int kTr2SmemBytes = kTr2Glwe * kTr2GlweSmem + 1024;  // + pass-2 twiddle table
 
 __device__ __forceinline__ void unit_sync(int bar) { asm volatile("bar.sync %0, 128;" ::"r"(bar) : "memory"); }
 
@@ -1989,156 +953,7 @@ __device__ __forceinline__ uint64_t pair_pick(const u64x2 &A, int h)
     return (h & 2) ? (0ull - x) : x;
 }
 
-__global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v2(const uint64_t *__restrict__ in,
-                                                                 uint64_t *__restrict__ out, int count, int from_acc,
-                                                                 const double *__restrict__ auto_f,
-                                                                 const double *__restrict__ twtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gl = threadIdx.x >> 7;
-    const int sub = (threadIdx.x >> 6) & 1;
-    const int t = threadIdx.x & 63;
-    const int idx = blockIdx.x * kTr2Glwe + gl;
-    cplx *t2tab = reinterpret_cast<cplx *>(smem_raw + (size_t)kTr2Glwe * kTr2GlweSmem);
-    fill_t2_table(t2tab, twtab, threadIdx.x);
-    __syncthreads();
-    if (idx >= count) return;
-    const cplx *t2s = t2tab + (t & 7);
-    unsigned char *base = smem_raw + (size_t)gl * kTr2GlweSmem;
-    u64x2 *cur = reinterpret_cast<u64x2 *>(base);
-    Group g;
-    g.t = t;
-    g.bar = 1 + gl * 2 + sub;
-    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8 + sub * 16384);
-    g.scr1 = g.scr0 + 512;
-    g.flip = 0;
-    cplx *X = reinterpret_cast<cplx *>(base + kGlweWords * 8 + 32768);  // [buf 2][sub 2][512]
-    const int ubar = 5 + gl;
-    Twiddles tw;
-    load_twiddles(tw, twtab, t);
-
-    // load (pair layout); from_acc fuses ggsw_conv.rs:302-314
-    {
-        const int u = threadIdx.x & 127;
-        if (from_acc) {
-            const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
-            const int lvl = idx % kCbsLevel;
-            for (int w = u; w < 3 * 512; w += 128) {
-                const int p = w >> 9, jj = w & 511;
-                cur[w] = u64x2{glev_pre_word(acc, lvl, p, jj), glev_pre_word(acc, lvl, p, jj + 512)};
-            }
-        } else {
-            const uint64_t *src = in + (size_t)idx * kGlweWords;
-            for (int w = u; w < 3 * 512; w += 128) {
-                const int p = w >> 9, jj = w & 511;
-                cur[w] = u64x2{src[p * 1024 + jj], src[p * 1024 + jj + 512]};
-            }
-        }
-    }
-    unit_sync(ubar);
-
-#pragma unroll 1
-    for (int s = 0; s < 10; s++) {
-        const int kinv = c_kappa_inv[s];
-        // ---- phase 0: every permuted read of this step (X -> X^kappa, utils.rs:475-490) ----
-        uint64_t pk[16];
-        {
-            const u64x2 *p = cur + sub * 512;  // mask polynomial i = sub
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int jj = t + 64 * m;
-                const int e = (jj * kinv) & 2047;
-                const u64x2 A = p[e & 511];
-                const int h = e >> 9;
-                pk[2 * m] = pack_digits<13, 3, uint64_t>(pair_pick(A, h));
-                pk[2 * m + 1] = pack_digits<13, 3, uint64_t>(pair_pick(A, (h + kinv) & 3));
-            }
-        }
-        u64x2 nb[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int jj = t + 64 * (4 * sub + q);
-            const int e = (jj * kinv) & 2047;
-            const u64x2 A = cur[1024 + (e & 511)];
-            const int h = e >> 9;
-            const u64x2 own = cur[1024 + jj];
-            nb[q] = u64x2{own.lo + pair_pick(A, h), own.hi + pair_pick(A, (h + kinv) & 3)};
-        }
-        unit_sync(ubar);
-        // keyswitch output starts as (0, 0, body(X^kappa)) and is added to the input (automorphism.rs:225-229)
-#pragma unroll
-        for (int q = 0; q < 4; q++) cur[1024 + t + 64 * (4 * sub + q)] = nb[q];
-
-        // ---- phase 1: 3 digit levels of the own mask polynomial; accumulate the own limb over both polynomials ----
-        cplx acc[3][8];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
-#pragma unroll 1
-        for (int tt = 0; tt < 3; tt++) {
-            const int lev = 2 - tt;
-            cplx v[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++)
-                v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m], tt)),
-                            i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m + 1], tt))};
-            fwd_fft_s(v, g, tw, t2s);
-            cplx *Xw = X + ((tt & 1) * 2 + sub) * 512 + t;
-            const cplx *Xr = X + ((tt & 1) * 2 + (1 - sub)) * 512 + t;
-#pragma unroll
-            for (int k3 = 0; k3 < 8; k3++) Xw[k3 * 64] = v[k3];
-            unit_sync(ubar);
-            // key layout [10][in 2][split 2][level 3][col 3]; limb index = sub
-            const double *k_own = auto_f + (size_t)((((s * 2 + sub) * 2 + sub) * 3 + lev) * 3) * kFourierPolyDoubles;
-            const double *k_oth = auto_f + (size_t)((((s * 2 + (1 - sub)) * 2 + sub) * 3 + lev) * 3) * kFourierPolyDoubles;
-            mul_acc<3>(acc, v, k_own, t);
-#pragma unroll
-            for (int k3 = 0; k3 < 8; k3++) {
-                const cplx o = Xr[k3 * 64];
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    cfma(acc[c][k3], o, ldg_cplx(k_oth + (size_t)c * kFourierPolyDoubles + (size_t)(k3 * 64 + t) * 2));
-            }
-        }
-        // ---- phase 2: inverse, torus rounding, hi limb << 41 (fourier_glwe_keyswitch.rs:323-341) ----
-        const int shift = sub ? 41 : 0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            inv_fft_s(acc[c], g, tw, t2s);
-            u64x2 *p = cur + c * 512;
-            if (sub == 0) {
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    u64x2 w = p[t + 64 * m];
-                    w.lo += torus_from_scaled(acc[c][m].x);
-                    w.hi += torus_from_scaled(acc[c][m].y);
-                    p[t + 64 * m] = w;
-                }
-            }
-            unit_sync(ubar);  // A's update of column c is complete before B adds its limb
-            if (sub == 1) {
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    u64x2 w = p[t + 64 * m];
-                    w.lo += torus_from_scaled(acc[c][m].x) << shift;
-                    w.hi += torus_from_scaled(acc[c][m].y) << shift;
-                    p[t + 64 * m] = w;
-                }
-            }
-        }
-        unit_sync(ubar);
-    }
-    uint64_t *dst = out + (size_t)idx * kGlweWords;
-    for (int w = threadIdx.x & 127; w < 3 * 512; w += 128) {
-        const u64x2 x = cur[w];
-        const int c = w >> 9, jj = w & 511;
-        dst[c * 1024 + jj] = x.lo;
-        dst[c * 1024 + jj + 512] = x.hi;
-    }
-}
-
-// ---- trace v3: v2 + automorphism-key tiles staged through a TMA ring --------------------------------
+// ---- automorphism-key tiles staged through a TMA ring -------------------------------------------------
 // ncu r01 (profiles/r01_final_ncu_full.csv) on v2: long-scoreboard (48 dependent 16-byte key loads from L2
 // per thread per digit level) was the top stall at 31 % of warp time.  The four key tiles of a digit
 // level - (input poly i, limb) in {0,1}^2, 24,576 B each - are now fetched once per CTA with
@@ -2150,10 +965,9 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v2(const uint64_t *
 constexpr int kTr3UnitSmem = kGlweWords * 8 + 2 * 8192 + 2 * 8192;  // cur 24 KB + 2 tiles + exchange = 56 KB
 constexpr int kTr3SmemBytes = kTr2Glwe * kTr3UnitSmem + 4 * kBrTileBytes + 1024 + 64;
 
-// XCH: shuffle-exchange transforms (fft512.cuh "x"): one shared-memory transpose and one sub-group barrier per
+// Transforms are the shuffle-exchange ones (fft512.cuh "x"): one shared-memory transpose and one sub-group barrier per
 // transform instead of two; both sub-groups produce spectra with the same per-lane phase, so the exchange tile and
 // the (plain-layout) key tiles are used unchanged.
-template <bool XCH>
 __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *__restrict__ in,
                                                                  uint64_t *__restrict__ out, int count, int from_acc,
                                                                  const double *__restrict__ auto_f,
@@ -2169,8 +983,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + 4 * kBrTileBytes + 1024);
     uint64_t *empty = full + 4;
     const int active_units = min(kTr2Glwe, count - blockIdx.x * kTr2Glwe);
-    if (XCH) fill_t2x_table(t2tab, twtab, threadIdx.x);
-    else fill_t2_table(t2tab, twtab, threadIdx.x);
+    fill_t2x_table(t2tab, twtab, threadIdx.x);
     if (threadIdx.x == 0) {
         for (int b = 0; b < 4; b++) {
             mbar_init(full + b, 1);
@@ -2220,8 +1033,7 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     const int sbar = 1 + gl * 2 + sub;
     const int ubar = 5 + gl;
     Twiddles tw;
-    if (XCH) load_twiddles_x(tw, twtab, t);
-    else load_twiddles(tw, twtab, t);
+    load_twiddles_x(tw, twtab, t);
     {
         const int u = threadIdx.x & 127;
         if (from_acc) {
@@ -2291,15 +1103,9 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
                 want = -1;
             }
             __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-            if (XCH) {
-                fwd_p2x_s(v, scr, t2s, t);
-                exchange8<-1>(v, t & 7);
-                fwd_p3x(v);
-            } else {
-                fwd_p2_s(v, scr, t2s, t);
-                group_sync(sbar);
-                fwd_p3(v, scr, t);
-            }
+            fwd_p2x_s(v, scr, t2s, t);
+            exchange8<-1>(v, t & 7);
+            fwd_p3x(v);
             cplx *Xw = X + sub * 512 + t;
             const cplx *Xr = X + (1 - sub) * 512 + t;
 #pragma unroll
@@ -2335,25 +1141,14 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
         const int shift = sub ? 41 : 0;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            if (XCH) {
-                inv_p3x(acc[c]);
-                exchange8<1>(acc[c], t & 7);
-                if (producer && want >= 0) {
-                    produce(want, false);
-                    want = -1;
-                }
-                __syncwarp();
-                inv_p2x_s(acc[c], scr, t2s, t);
-            } else {
-                inv_p3(acc[c], scr, t);
-                group_sync(sbar);
-                if (producer && want >= 0) {
-                    produce(want, false);
-                    want = -1;
-                }
-                __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-                inv_p2_s(acc[c], scr, t2s, t);
+            inv_p3x(acc[c]);
+            exchange8<1>(acc[c], t & 7);
+            if (producer && want >= 0) {
+                produce(want, false);
+                want = -1;
             }
+            __syncwarp();
+            inv_p2x_s(acc[c], scr, t2s, t);
             group_sync(sbar);
             inv_p1(acc[c], scr, tw, t);
             u64x2 *p = cur + c * 512;
@@ -2405,25 +1200,10 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
             kinv[i] = x;
         }
         cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
-        cudaFuncSetAttribute(k_trace_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr2SmemBytes);
-        cudaFuncSetAttribute(k_trace_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
-        cudaFuncSetAttribute(k_trace_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
+        cudaFuncSetAttribute(k_trace_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
         init = true;
     }
-    static int variant = -1;
-    if (variant < 0) {
-        const char *e = getenv("CBS_TRACE_VARIANT");
-        variant = e ? atoi(e) : 4;  // 2 = LDG keys, 3 = TMA ring, 4 = TMA ring + shuffle-exchange transforms
-    }
-    if (variant >= 4)
-        k_trace_v3<true><<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
-                                                                                                     K.auto_f, K.tw);
-    else if (variant == 3)
-        k_trace_v3<false><<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc,
-                                                                                                      K.auto_f, K.tw);
-    else
-        k_trace_v2<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr2SmemBytes, s>>>(in, out, count, from_acc,
-                                                                                               K.auto_f, K.tw);
+    k_trace_v3<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc, K.auto_f, K.tw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2458,90 +1238,7 @@ __device__ __forceinline__ void emit_row_poly(const uint64_t lo[8], const uint64
     }
 }
 
-__global__ void __launch_bounds__(64 * kSsGroups, 1) k_scheme_switch(const uint64_t *__restrict__ glev,
-                                                                      uint64_t *__restrict__ ggsw_std,
-                                                                      double *__restrict__ ggsw_f, int count,
-                                                                      const double *__restrict__ ss_f,
-                                                                      const double *__restrict__ twtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6;
-    const int idx = blockIdx.x * kSsGroups + gi;  // (ciphertext, level)
-    if (idx >= count * kCbsLevel) return;
-    unsigned char *base = smem_raw + (size_t)gi * kSsGroupSmem;
-    uint64_t *gl = reinterpret_cast<uint64_t *>(base);
-    Group g;
-    g.t = threadIdx.x & 63;
-    g.bar = 1 + gi;
-    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
-    g.scr1 = g.scr0 + 512;
-    g.flip = 0;
-    Twiddles tw;
-    load_twiddles(tw, twtab, g.t);
-    const int t = g.t;
-    const uint64_t *src = glev + (size_t)idx * kGlweWords;
-    for (int w = t; w < kGlweWords; w += 64) gl[w] = src[w];
-    group_sync(g.bar);
-    // GGSW layout [level][row][poly]; idx = ct*7 + level
-    uint64_t *std_base = ggsw_std ? ggsw_std + (size_t)idx * 3 * kGlweWords : nullptr;
-    double *f_base = ggsw_f ? ggsw_f + (size_t)idx * 9 * kFourierPolyDoubles : nullptr;
-
-#pragma unroll 1
-    for (int i = 0; i < 2; i++) {
-        cplx acc[3][8];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
-#pragma unroll 1
-        for (int r = 0; r < 3; r++) {
-            uint64_t pk[16];
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                pk[2 * m] = pack_digits<17, 2, uint64_t>(gl[r * 1024 + t + 64 * m]);
-                pk[2 * m + 1] = pack_digits<17, 2, uint64_t>(gl[r * 1024 + t + 64 * m + 512]);
-            }
-#pragma unroll 1
-            for (int tt = 0; tt < 2; tt++) {
-                const int lev = 1 - tt;
-                cplx v[8];
-#pragma unroll
-                for (int m = 0; m < 8; m++)
-                    v[m] = cplx{i32_to_double(unpack_digit<17, uint64_t>(pk[2 * m], tt)),
-                                i32_to_double(unpack_digit<17, uint64_t>(pk[2 * m + 1], tt))};
-                fwd_fft(v, g, tw);
-                const double *key = ss_f + (size_t)(((i * 2 + lev) * 3 + r) * 3) * kFourierPolyDoubles;
-                mul_acc<3>(acc, v, key, t);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            inv_fft(acc[c], g, tw);
-            uint64_t lo[8], hi[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                lo[m] = torus_from_scaled(acc[c][m].x);
-                hi[m] = torus_from_scaled(acc[c][m].y);
-            }
-            emit_row_poly(lo, hi, std_base ? std_base + (size_t)(i * 3 + c) * 1024 : nullptr,
-                          f_base ? f_base + (size_t)(i * 3 + c) * kFourierPolyDoubles : nullptr, g, tw);
-        }
-    }
-    // row k = the GLEV level itself (ggsw_conv.rs:191)
-#pragma unroll 1
-    for (int c = 0; c < 3; c++) {
-        uint64_t lo[8], hi[8];
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            lo[m] = gl[c * 1024 + t + 64 * m];
-            hi[m] = gl[c * 1024 + t + 64 * m + 512];
-        }
-        emit_row_poly(lo, hi, std_base ? std_base + (size_t)(6 + c) * 1024 : nullptr,
-                      f_base ? f_base + (size_t)(6 + c) * kFourierPolyDoubles : nullptr, g, tw);
-    }
-}
-
-// v2: the 12 scheme-switching-key row tiles go through the 2-deep TMA ring shared by the CTA's groups
+// the 12 scheme-switching-key row tiles go through the 2-deep TMA ring shared by the CTA's groups
 constexpr int kSs2SmemBytes = kSsSmemBytes + kBrRing * kBrTileBytes + 64;
 __global__ void __launch_bounds__(64 * kSsGroups, 1) k_scheme_switch_v2(const uint64_t *__restrict__ glev,
                                                                       uint64_t *__restrict__ ggsw_std,
@@ -2669,22 +1366,11 @@ void launch_scheme_switch(const DeviceKeys &K, const uint64_t *glev, uint64_t *g
     cudaGetDevice(&attr_dev);
     bool &attr = attr_done[attr_dev & 63];
     if (!attr) {
-        cudaFuncSetAttribute(k_scheme_switch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemBytes);
         cudaFuncSetAttribute(k_scheme_switch_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs2SmemBytes);
         attr = true;
     }
     const int groups = count * kCbsLevel;
-    static int variant = -1;
-    if (variant < 0) {
-        const char *e = getenv("CBS_SS_VARIANT");
-        variant = e ? atoi(e) : 2;
-    }
-    if (variant == 1)
-        k_scheme_switch<<<(groups + kSsGroups - 1) / kSsGroups, 64 * kSsGroups, kSsSmemBytes, s>>>(glev, ggsw_std, ggsw_f,
-                                                                                                     count, K.ss_f, K.tw);
-    else
-        k_scheme_switch_v2<<<(groups + kSsGroups - 1) / kSsGroups, 64 * kSsGroups, kSs2SmemBytes, s>>>(glev, ggsw_std, ggsw_f,
-                                                                                                         count, K.ss_f, K.tw);
+    k_scheme_switch_v2<<<(groups + kSsGroups - 1) / kSsGroups, 64 * kSsGroups, kSs2SmemBytes, s>>>(glev, ggsw_std, ggsw_f, count, K.ss_f, K.tw);
 }
 
 void launch_ggsw_to_fourier(const DeviceKeys &K, const uint64_t *ggsw_std, double *ggsw_f, int count, cudaStream_t s)
@@ -2732,65 +1418,8 @@ __device__ __forceinline__ void cbs_external_product(cplx (&out)[3][8], const do
     }
 }
 
-__global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8(const double *__restrict__ ggsw_f,
-                                                              const uint64_t *__restrict__ luts,
-                                                              const int *__restrict__ lut_index,
-                                                              const int *__restrict__ out_index,
-                                                              uint64_t *__restrict__ out, int njobs, int accs_per_byte,
-                                                              const double *__restrict__ twtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6;
-    const int job = blockIdx.x * kLutGroups + gi;
-    if (job >= njobs) return;
-    unsigned char *base = smem_raw + (size_t)gi * kLutGroupSmem;
-    uint64_t *acc = reinterpret_cast<uint64_t *>(base);
-    Group g;
-    g.t = threadIdx.x & 63;
-    g.bar = 1 + gi;
-    g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
-    g.scr1 = g.scr0 + 512;
-    g.flip = 0;
-    Twiddles tw;
-    load_twiddles(tw, twtab, g.t);
-    const int t = g.t;
-    const uint64_t *src = luts + (size_t)lut_index[job] * kGlweWords;
-    for (int w = t; w < kGlweWords; w += 64) acc[w] = src[w];
-    group_sync(g.bar);
-    const double *bits = ggsw_f + (size_t)(job / accs_per_byte) * 8 * kGgswWords;
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-        const int d = 1 << i;
-        cplx o[3][8];
-        cbs_external_product(o, bits + (size_t)i * kGgswWords, g, tw, [&](int r, int j) {
-            return neg_read(acc + r * 1024, (j + d) & 2047) - acc[r * 1024 + j];  // acc * X^-d - acc
-        });
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            inv_fft(o[c], g, tw);
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                acc[c * 1024 + t + 64 * m] += torus_from_scaled(o[c][m].x);
-                acc[c * 1024 + t + 64 * m + 512] += torus_from_scaled(o[c][m].y);
-            }
-        }
-    }
-    group_sync(g.bar);
-    // sample extraction at degree 256*q  ->  LWE(2048)
-    for (int q = 0; q < 4; q++) {
-        const int T = 256 * q;
-        uint64_t *o = out + (size_t)(out_index[job] + q) * kLweBig;
-        for (int w = t; w < 2048; w += 64) {
-            const int c = w >> 10, j = w & 1023;
-            const uint64_t *mp = acc + c * 1024;
-            o[w] = (j <= T) ? mp[T - j] : (0ull - mp[1024 + T - j]);
-        }
-        if (t == 0) o[2048] = acc[2048 + T];
-    }
-}
-
 // ---- LUT ladder with gathered selectors (inner-product circuit, host/ip_plan.h) ---------------------------
-// Same ladder as k_lut8, but the 8 selector GGSWs of a job are picked by index (sel[job][i], -1 = the
+// Same ladder as k_lut8_v2 (below), but the 8 selector GGSWs of a job are picked by index (sel[job][i], -1 = the
 // selector is the constant 0: the CMux is the identity and is skipped), so one circuit-bootstrapped bit can
 // feed several ladders and ladders may have fewer than 8 inputs.
 __global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8_gather(const double *__restrict__ ggsw_f,
@@ -3076,26 +1705,21 @@ void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts
     int attr_dev = 0;
     cudaGetDevice(&attr_dev);
     bool &attr = attr_done[attr_dev & 63];
-    static int variant = 2;
     if (!attr) {
-        cudaFuncSetAttribute(k_lut8, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutSmemBytes);
         cudaFuncSetAttribute(k_lut8_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kLut2SmemBytes);
-        if (const char *e = getenv("CBS_LUT_VARIANT")) variant = atoi(e);
         attr = true;
     }
-    int groups = 0;
+    // `groups` jobs per CTA must all belong to the same byte: the largest divisor of accs_per_byte that fits a CTA
+    int groups = 1;
     for (int gsz = kLutGroups; gsz >= 1; gsz--)
         if (accs_per_byte % gsz == 0) {
             groups = gsz;
             break;
         }
-    if (variant == 1 || njobs % accs_per_byte != 0)
-        k_lut8<<<(njobs + kLutGroups - 1) / kLutGroups, 64 * kLutGroups, kLutSmemBytes, s>>>(ggsw_f, luts, lut_index,
-                                                                                              out_index, out, njobs,
-                                                                                              accs_per_byte, K.tw);
-    else
-        k_lut8_v2<<<njobs / groups, 64 * kLutGroups, kLut2SmemBytes, s>>>(ggsw_f, luts, lut_index, out_index, out, njobs,
-                                                                          accs_per_byte, K.tw, groups, trivial);
+    // njobs is a whole number of bytes for every caller (cbs_api.cu); a ragged tail would read another byte's selectors
+    if (njobs % accs_per_byte != 0) return;
+    k_lut8_v2<<<njobs / groups, 64 * kLutGroups, kLut2SmemBytes, s>>>(ggsw_f, luts, lut_index, out_index, out, njobs, accs_per_byte, K.tw,
+                                                                      groups, trivial);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -36,16 +36,12 @@ struct DeviceKeys {
     const double *auto_f;   // 10*2*2*3*3 Fourier polys
     const double *ss_f;     // 2*2*3*3 Fourier polys
     const double *ksk_f;    // 8*3*4*128 complex
-    const double *bsk_w;    // 768*9 Fourier polys in the W layout of fftw512.cuh ([rho 16][lane 32] complex), or null
-    const double *wtab;     // per-lane tables of the one-warp transform (fft_tables.h make_w_tables)
 };
 
 // generic std -> Fourier conversion of `npoly` polynomials (N = 1024).
 // mode 0: whole word; mode 1: low `split` bits; mode 2: word >> split.
 void launch_std_to_fourier(const uint64_t *in, double *out, int npoly, int mode, int split, const double *tw,
                            cudaStream_t s);
-// std -> Fourier in the W layout of fftw512.cuh (true spectra / 512, [poly][rho][lane])
-void launch_std_to_fourier_w(const uint64_t *in, double *out, int npoly, const double *wtab, cudaStream_t s);
 // KSK (N' = 256) std -> Fourier
 void launch_ksk_to_fourier(const uint64_t *in, double *out, int npoly, const double *tw128, cudaStream_t s);
 

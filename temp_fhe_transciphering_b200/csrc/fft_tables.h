@@ -43,35 +43,3 @@ inline std::vector<double> make_twiddle_table()
 }
 
 }  // namespace cbs
-
-#include "fftw512.cuh"
-namespace cbs {
-
-// Per-lane tables of the one-warp transform (fftw512.cuh): [32 lanes][kWTabCplx] complex doubles, lane t = b + 4a:
-//   C[m]    = exp(i pi 32 m / 1024) * W8^(a m)                          (twist part of register m, output rotation of pass 1)
-//   T1[k]   = exp(i pi t / 1024) * W512^(t k2) * i^(b x),  k = u + 2x,  k2 = (k + 2a) mod 16
-//   T2[k]   = W8^(a ka) * W32^(b ka),                      ka = (k + 2b) mod 8
-inline std::vector<double> make_w_tables()
-{
-    std::vector<double> tab((size_t)32 * kWTabCplx * 2);
-    const long double two_pi = 6.283185307179586476925286766559005768L;
-    auto put = [&](int lane, int idx, long double turns) {  // exp(2 pi i * turns)
-        tab[((size_t)lane * kWTabCplx + idx) * 2] = (double)cosl(two_pi * turns);
-        tab[((size_t)lane * kWTabCplx + idx) * 2 + 1] = (double)sinl(two_pi * turns);
-    };
-    for (int t = 0; t < 32; t++) {
-        const int b = t & 3, a = t >> 2;
-        for (int m = 0; m < 16; m++) put(t, kWTabC + m, (long double)(32 * m) / 2048.0L - (long double)((a * m) & 7) / 8.0L);
-        for (int k = 0; k < 16; k++) {
-            const int x = k >> 1, k2 = (k + 2 * a) & 15;
-            put(t, kWTabT1 + k, (long double)t / 2048.0L - (long double)((t * k2) & 511) / 512.0L + (long double)((b * x) & 3) / 4.0L);
-        }
-        for (int k = 0; k < 8; k++) {
-            const int ka = (k + 2 * b) & 7;
-            put(t, kWTabT2 + k, -(long double)((a * ka) & 7) / 8.0L - (long double)((b * ka) & 31) / 32.0L);
-        }
-    }
-    return tab;
-}
-
-}  // namespace cbs

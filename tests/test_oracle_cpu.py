@@ -35,16 +35,6 @@ def test_fft_core_cpu_emulation(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
 
 
-def test_warp_fft_cpu_emulation(tmp_path):
-    """The one-warp transform (fftw512.cuh: 16 points per thread, shuffle exchanges, tensor-memory tables) executed on the
-    CPU lane by lane: bin map and unapplied phase against a naive DFT, round trip, negacyclic product against true spectra."""
-    exe = tmp_path / "fftw_emul"
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "temp_fhe_transciphering_b200", "csrc"),
-                           os.path.join(ROOT, "tests", "cpu_emul", "fftw_emul.cpp"), "-o", str(exe)])
-    out = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert out.returncode == 0, out.stdout + out.stderr
-
-
 def test_oracle_primitives(orc):
     L = orc.lib()
     # modulus switch: multiples of 8 in [0, 2N]  (tfhe fast_pbs_modulus_switch, log_lut_count = 3)
