@@ -80,6 +80,10 @@ int cbs_keyset_from_arrays(const uint64_t *bsk, const uint64_t *ksk, const uint6
  * noise; cbs_lib/src/keygen.rs:187-243, src/bin/client_key_generation.rs:20-86).  Client-side helper
  * for tests and benches: the reference's own keygen is unseeded. */
 int cbs_keyset_generate(uint64_t seed, cbs_keyset **out);
+/* The same generation with secrets, masks and noise drawn from ChaCha20 keyed with 256 bits of getrandom(2): what
+ * bin/client_key_generation uses when no seed is given (the harness expects fresh keys on every run,
+ * harness/run_submission.py:74-77).  The seeded variant above is deterministic and NOT cryptographically secure. */
+int cbs_keyset_generate_os_entropy(cbs_keyset **out);
 void cbs_keyset_free(cbs_keyset *ks);
 const uint64_t *cbs_keyset_bsk(const cbs_keyset *ks);
 const uint64_t *cbs_keyset_ksk(const cbs_keyset *ks);
@@ -95,6 +99,8 @@ int cbs_trans_key_save(const char *path, const uint64_t *k10_9, const uint64_t *
  * rounds 10/9 encrypted LUTs, rounds 8..1 and 0 trivial LUTs, for ECB block decryption. */
 int cbs_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *k10_9,
                            uint64_t *k8_1, uint64_t *k0);
+int cbs_trans_key_generate_os_entropy(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t *k10_9, uint64_t *k8_1,
+                                      uint64_t *k0);
 /* Forward-direction transciphering key for CTR mode (the harness uses CTR for sizes 1/2,
  * harness/aes_keygen_and_encrypt.py:45-55, which the reference does not implement).  Keyed S-boxes as
  * cbs_lib/src/aes_ref.rs:334-380: kf_first [3 (x1,x2,x3)][16][2] encrypted GLWE LUTs of
@@ -103,6 +109,8 @@ int cbs_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint
  * AllRdKeys with 3-tuples. */
 int cbs_fwd_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *kf_first,
                                uint64_t *kf_mid, uint64_t *kf_last);
+int cbs_fwd_trans_key_generate_os_entropy(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t *kf_first, uint64_t *kf_mid,
+                                          uint64_t *kf_last);
 int cbs_fwd_trans_key_load(const char *path, uint64_t *kf_first, uint64_t *kf_mid, uint64_t *kf_last);
 int cbs_fwd_trans_key_save(const char *path, const uint64_t *kf_first, const uint64_t *kf_mid, const uint64_t *kf_last);
 /* LweCiphertextList<Vec<u64>> result.bin */
@@ -124,6 +132,9 @@ int cbs_encrypt_bits_small(const cbs_keyset *ks, const uint8_t *bits, int count,
  * Device context: uploads the keys, converts them to the Fourier domain ON THE GPU
  * (replaces server_encrypted_aes_decryption.rs:645-687). */
 int cbs_device_count(int *count); /* visible CUDA devices (CBS_ERR_CUDA if the driver is absent) */
+/* create the CUDA primary context of `device` now (cudaSetDevice + cudaFree(0)) so that a caller can account for
+ * driver start-up separately from cbs_ctx_create; optional - cbs_ctx_create does it implicitly otherwise. */
+int cbs_device_init(int device);
 int cbs_ctx_create(const cbs_keyset *ks, int device, cbs_ctx **out);
 void cbs_ctx_destroy(cbs_ctx *ctx);
 int cbs_ctx_device(const cbs_ctx *ctx);

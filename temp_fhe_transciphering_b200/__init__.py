@@ -126,9 +126,14 @@ class KeySet:
             self._h = None
 
     @classmethod
-    def generate(cls, seed):
+    def generate(cls, seed=None):
+        """seed = None: ChaCha20 keyed by getrandom(2) (fresh keys, what the stage executable does without a seed);
+        an integer: the deterministic, not cryptographically secure test generator."""
         h = ctypes.c_void_p()
-        _check(lib().cbs_keyset_generate(ctypes.c_uint64(seed), ctypes.byref(h)), "cbs_keyset_generate")
+        if seed is None:
+            _check(lib().cbs_keyset_generate_os_entropy(ctypes.byref(h)), "cbs_keyset_generate_os_entropy")
+        else:
+            _check(lib().cbs_keyset_generate(ctypes.c_uint64(seed), ctypes.byref(h)), "cbs_keyset_generate")
         return cls(h.value)
 
     @classmethod

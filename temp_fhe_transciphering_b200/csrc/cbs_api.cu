@@ -413,6 +413,13 @@ int cbs_device_count(int *count)
     return CBS_OK;
 }
 
+int cbs_device_init(int device)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(nullptr));
+    return CBS_OK;
+}
+
 int cbs_ctx_create(const cbs_keyset *ks, int device, cbs_ctx **out)
 {
     if (!ks || !out) {

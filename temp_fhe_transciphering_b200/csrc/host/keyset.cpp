@@ -20,6 +20,7 @@
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <sys/random.h>
 #include <sys/stat.h>
 #include <thread>
 #include <vector>
@@ -211,9 +212,38 @@ static double fourier_to_limb(const double *in, uint64_t *limb, double max_value
 }
 
 // ------------------------------------------------------------------------------------------------
-// randomness: xoshiro256++ streams keyed by (seed, stream id) so results do not depend on threading
+// randomness.  Two engines behind one interface, both as independent streams keyed by a stream id so results do not
+// depend on threading:
+//   * RngSource(seed): xoshiro256++ - deterministic, NOT cryptographically secure; only for reproducible tests, benches
+//     and golden vectors (explicit seed argument / CBS_SEED);
+//   * RngSource::os_entropy(): ChaCha20 (RFC 8439 block function) keyed with 256 bits from getrandom(2), stream id as
+//     nonce - what the stage executables use when no seed is given, like the reference's own client
+//     (client_key_generation.rs:91-96 new_seeder(); harness/run_submission.py:74-77: keys differ on every run).
+struct RngSource {
+    bool secure = false;
+    uint64_t seed = 0;
+    uint32_t key[8] = {0};
+    explicit RngSource(uint64_t s) : seed(s) {}
+    static bool os_entropy(RngSource &out)
+    {
+        out.secure = true;
+        size_t got = 0;
+        unsigned char *p = reinterpret_cast<unsigned char *>(out.key);
+        while (got < sizeof out.key) {
+            ssize_t n = getrandom(p + got, sizeof out.key - got, 0);
+            if (n <= 0) return false;
+            got += (size_t)n;
+        }
+        return true;
+    }
+};
+
 struct Rng {
-    uint64_t s[4];
+    bool secure;
+    uint64_t s[4];             // xoshiro256++ state
+    uint32_t cc[16];           // ChaCha20 input block (constants, key, counter, nonce)
+    uint64_t buf[8];
+    int have = 0;
     static uint64_t splitmix(uint64_t &x)
     {
         uint64_t z = (x += 0x9E3779B97F4A7C15ull);
@@ -221,14 +251,50 @@ struct Rng {
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         return z ^ (z >> 31);
     }
-    Rng(uint64_t seed, uint64_t stream)
+    Rng(const RngSource &src, uint64_t stream) : secure(src.secure)
     {
-        uint64_t x = seed * 0xD1342543DE82EF95ull + stream * 0xA0761D6478BD642Full + 0x1234567ull;
-        for (auto &v : s) v = splitmix(x);
+        if (secure) {
+            cc[0] = 0x61707865, cc[1] = 0x3320646e, cc[2] = 0x79622d32, cc[3] = 0x6b206574;  // "expand 32-byte k"
+            for (int i = 0; i < 8; i++) cc[4 + i] = src.key[i];
+            cc[12] = 0;
+            cc[13] = (uint32_t)stream;
+            cc[14] = (uint32_t)(stream >> 32);
+            cc[15] = 0;
+        } else {
+            uint64_t x = src.seed * 0xD1342543DE82EF95ull + stream * 0xA0761D6478BD642Full + 0x1234567ull;
+            for (auto &v : s) v = splitmix(x);
+        }
     }
     static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    static uint32_t rotl32(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }
+    void chacha_block()
+    {
+        uint32_t x[16];
+        memcpy(x, cc, sizeof x);
+#define CBS_QR(a, b, c, d)                                                                       \
+    x[a] += x[b], x[d] = rotl32(x[d] ^ x[a], 16), x[c] += x[d], x[b] = rotl32(x[b] ^ x[c], 12), \
+        x[a] += x[b], x[d] = rotl32(x[d] ^ x[a], 8), x[c] += x[d], x[b] = rotl32(x[b] ^ x[c], 7)
+        for (int r = 0; r < 10; r++) {
+            CBS_QR(0, 4, 8, 12);
+            CBS_QR(1, 5, 9, 13);
+            CBS_QR(2, 6, 10, 14);
+            CBS_QR(3, 7, 11, 15);
+            CBS_QR(0, 5, 10, 15);
+            CBS_QR(1, 6, 11, 12);
+            CBS_QR(2, 7, 8, 13);
+            CBS_QR(3, 4, 9, 14);
+        }
+#undef CBS_QR
+        for (int i = 0; i < 8; i++) buf[i] = (uint64_t)(x[2 * i] + cc[2 * i]) | ((uint64_t)(x[2 * i + 1] + cc[2 * i + 1]) << 32);
+        if (++cc[12] == 0) cc[15]++;  // 2^32 blocks of 64 bytes per (stream, cc[15]): far beyond any use here
+        have = 8;
+    }
     uint64_t next()
     {
+        if (secure) {
+            if (!have) chacha_block();
+            return buf[--have];
+        }
         uint64_t r = rotl(s[0] + s[3], 23) + s[0];
         uint64_t t = s[1] << 17;
         s[2] ^= s[0];
@@ -621,7 +687,7 @@ int cbs_keyset_save_dir(const cbs_keyset *ks, const char *io_dir, int with_secre
     return CBS_OK;
 }
 
-int cbs_keyset_generate(uint64_t seed, cbs_keyset **out)
+static int keyset_generate_impl(const RngSource &src, cbs_keyset **out)
 {
     if (!out) return CBS_ERR_ARG;
     auto *k = new cbs_keyset;
@@ -631,14 +697,14 @@ int cbs_keyset_generate(uint64_t seed, cbs_keyset **out)
     k->ss.assign(CBS_SS_WORDS, 0);
     k->lwe_sk_small.resize(768);
     k->glwe_sk.resize(2048);
-    Rng srng(seed, 0);
+    Rng srng(src, 0);
     for (auto &b : k->lwe_sk_small) b = srng.next() >> 63;
     for (auto &b : k->glwe_sk) b = srng.next() >> 63;
     const uint64_t *S = k->glwe_sk.data();
 
     // bootstrap key: GGSW(s_i) under glwe_sk, B = 2^23, l = 1 (keygen.rs:213-221)
     parallel_for(768, [&](int i) {
-        Rng rng(seed, 1000 + (uint64_t)i);
+        Rng rng(src, 1000 + (uint64_t)i);
         const uint64_t m = k->lwe_sk_small[i];
         std::vector<uint64_t> pt(1024);
         for (int row = 0; row < 3; row++) {
@@ -659,7 +725,7 @@ int cbs_keyset_generate(uint64_t seed, cbs_keyset **out)
         std::vector<uint64_t> pt(256);
         for (int i = 0; i < 8; i++)
             for (int lev = 0; lev < 3; lev++) {
-                Rng rng(seed, 5000 + (uint64_t)(i * 3 + lev));
+                Rng rng(src, 5000 + (uint64_t)(i * 3 + lev));
                 const int log_scale = 64 - 4 * (lev + 1);
                 for (int j = 0; j < 256; j++) pt[j] = (0ull - S[i * 256 + j]) << log_scale;
                 glwe_encrypt(k->ksk.data() + ((size_t)i * 3 + lev) * 4 * 256, pt.data(), k->lwe_sk_small.data(), 3, 256,
@@ -674,7 +740,7 @@ int cbs_keyset_generate(uint64_t seed, cbs_keyset **out)
         for (int i = 0; i < 2; i++) {
             eval_x_k(before.data(), S + i * 1024, 1024, kappa);
             for (int lev = 0; lev < 3; lev++) {
-                Rng rng(seed, 6000 + (uint64_t)((idx * 2 + i) * 3 + lev));
+                Rng rng(src, 6000 + (uint64_t)((idx * 2 + i) * 3 + lev));
                 const int log_scale = 64 - 13 * (lev + 1);
                 for (int j = 0; j < 1024; j++) pt[j] = (0ull - before[j]) << log_scale;
                 glwe_encrypt(k->autok.data() + (((size_t)idx * 2 + i) * 3 + lev) * 3072, pt.data(), S, 2, 1024, kStdGlwe,
@@ -688,7 +754,7 @@ int cbs_keyset_generate(uint64_t seed, cbs_keyset **out)
     for (int i = 0; i < 2; i++)
         for (int lev = 0; lev < 2; lev++)
             for (int col = 0; col < 3; col++) {
-                Rng rng(seed, 7000 + (uint64_t)((i * 2 + lev) * 3 + col));
+                Rng rng(src, 7000 + (uint64_t)((i * 2 + lev) * 3 + col));
                 uint64_t *ct = k->ss.data() + (((size_t)i * 2 + lev) * 3 + col) * 3072;
                 glwe_encrypt(ct, nullptr, S, 2, 1024, kStdGlwe, rng);
                 const int log_scale = 64 - 17 * (lev + 1);
@@ -699,8 +765,20 @@ int cbs_keyset_generate(uint64_t seed, cbs_keyset **out)
     return CBS_OK;
 }
 
-int cbs_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *k10_9,
-                           uint64_t *k8_1, uint64_t *k0)
+int cbs_keyset_generate(uint64_t seed, cbs_keyset **out) { return keyset_generate_impl(RngSource(seed), out); }
+
+int cbs_keyset_generate_os_entropy(cbs_keyset **out)
+{
+    RngSource src(0);
+    if (!RngSource::os_entropy(src)) {
+        set_error("getrandom failed");
+        return CBS_ERR_IO;
+    }
+    return keyset_generate_impl(src, out);
+}
+
+static int trans_key_generate_impl(const cbs_keyset *ks, const uint8_t aes_key[16], const RngSource &src, uint64_t *k10_9,
+                                   uint64_t *k8_1, uint64_t *k0)
 {
     if (!ks || ks->glwe_sk.empty() || !aes_key || !k10_9 || !k8_1 || !k0) {
         set_error("cbs_trans_key_generate: needs a keyset with the GLWE secret key");
@@ -713,7 +791,7 @@ int cbs_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint
     const uint64_t *S = ks->glwe_sk.data();
     parallel_for(4 * 16 * 2, [&](int id) {
         const int a = id & 1, b = (id >> 1) & 15, m = id >> 5;
-        Rng rng(seed, 9000 + (uint64_t)id);
+        Rng rng(src, 9000 + (uint64_t)id);
         std::vector<uint64_t> pt(1024);
         lut_plaintext(pt.data(), tab[b], a, mults[m]);
         glwe_encrypt(k10_9 + (size_t)id * 3072, pt.data(), S, 2, 1024, kStdGlwe, rng);
@@ -731,6 +809,23 @@ int cbs_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint
     for (int b = 0; b < 16; b++)
         for (int a = 0; a < 2; a++) lut_plaintext(k0 + ((size_t)b * 2 + a) * 3072 + 2048, tab[b], a, 0);
     return CBS_OK;
+}
+
+int cbs_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *k10_9,
+                           uint64_t *k8_1, uint64_t *k0)
+{
+    return trans_key_generate_impl(ks, aes_key, RngSource(seed), k10_9, k8_1, k0);
+}
+
+int cbs_trans_key_generate_os_entropy(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t *k10_9, uint64_t *k8_1,
+                                      uint64_t *k0)
+{
+    RngSource src(0);
+    if (!RngSource::os_entropy(src)) {
+        set_error("getrandom failed");
+        return CBS_ERR_IO;
+    }
+    return trans_key_generate_impl(ks, aes_key, src, k10_9, k8_1, k0);
 }
 
 int cbs_trans_key_load(const char *path, uint64_t *k10_9, uint64_t *k8_1, uint64_t *k0)
@@ -825,7 +920,7 @@ int cbs_trans_key_save(const char *path, const uint64_t *k10_9, const uint64_t *
 }
 
 // ---- forward direction (CTR mode) ----
-int cbs_fwd_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *kf_first,
+static int fwd_trans_key_generate_impl(const cbs_keyset *ks, const uint8_t aes_key[16], const RngSource &src, uint64_t *kf_first,
                                uint64_t *kf_mid, uint64_t *kf_last)
 {
     if (!ks || ks->glwe_sk.empty() || !aes_key || !kf_first || !kf_mid || !kf_last) {
@@ -839,7 +934,7 @@ int cbs_fwd_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], 
     const uint64_t *S = ks->glwe_sk.data();
     parallel_for(3 * 16 * 2, [&](int id) {
         const int a = id & 1, b = (id >> 1) & 15, m = id >> 5;
-        Rng rng(seed, 11000 + (uint64_t)id);
+        Rng rng(src, 11000 + (uint64_t)id);
         std::vector<uint64_t> pt(1024);
         lut_plaintext(pt.data(), tab[b], a, mults[m] == 1 ? 0 : mults[m]);
         glwe_encrypt(kf_first + (size_t)id * 3072, pt.data(), S, 2, 1024, kStdGlwe, rng);
@@ -861,6 +956,23 @@ int cbs_fwd_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], 
 }
 
 // Forward keys use the AllRdKeys bincode shape with 3-tuples (x1, x2, x3) and 8 middle rounds.
+int cbs_fwd_trans_key_generate(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t seed, uint64_t *kf_first,
+                               uint64_t *kf_mid, uint64_t *kf_last)
+{
+    return fwd_trans_key_generate_impl(ks, aes_key, RngSource(seed), kf_first, kf_mid, kf_last);
+}
+
+int cbs_fwd_trans_key_generate_os_entropy(const cbs_keyset *ks, const uint8_t aes_key[16], uint64_t *kf_first, uint64_t *kf_mid,
+                                          uint64_t *kf_last)
+{
+    RngSource src(0);
+    if (!RngSource::os_entropy(src)) {
+        set_error("getrandom failed");
+        return CBS_ERR_IO;
+    }
+    return fwd_trans_key_generate_impl(ks, aes_key, src, kf_first, kf_mid, kf_last);
+}
+
 int cbs_fwd_trans_key_save(const char *path, const uint64_t *kf_first, const uint64_t *kf_mid, const uint64_t *kf_last)
 {
     if (!path) return CBS_ERR_ARG;
@@ -1090,8 +1202,9 @@ int cbs_max_plan_check(const uint16_t *vals, int nvals, uint16_t *result, int64_
 
 static int encrypt_bits(const uint64_t *sk, int n, double std, const uint8_t *bits, int count, uint64_t seed, uint64_t *out)
 {
+    const RngSource src(seed);
     for (int c = 0; c < count; c++) {
-        Rng rng(seed, 20000 + (uint64_t)c);
+        Rng rng(src, 20000 + (uint64_t)c);
         uint64_t *ct = out + (size_t)c * (n + 1);
         uint64_t b = rng.noise(std) + ((uint64_t)(bits[c] & 1) << 63);
         for (int i = 0; i < n; i++) {

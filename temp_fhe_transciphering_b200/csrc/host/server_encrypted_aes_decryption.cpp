@@ -10,6 +10,7 @@
 #include "stage_common.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <thread>
 
@@ -17,6 +18,7 @@ int main(int argc, char **argv)
 {
     long size;
     if (!parse_size(argc, argv, &size)) return 1;
+    StageClock clk("server_encrypted_aes_decryption");
     const std::string io_dir = std::string("io/") + size_string(size);
     const std::string data_dir = std::string("datasets/") + size_string(size);
 
@@ -29,6 +31,7 @@ int main(int argc, char **argv)
 
     cbs_keyset *ks = nullptr;
     STAGE_TRY(cbs_keyset_load_dir(io_dir.c_str(), 0, &ks));
+    clk.mark("read_public_keys");
     const bool ctr_mode = size >= 1;
     std::vector<uint8_t> iv;
     if (ctr_mode && (!read_hex_file(data_dir + "/aes_iv.hex", iv) || iv.size() != 16)) {
@@ -41,6 +44,7 @@ int main(int argc, char **argv)
     if (ctr_mode) STAGE_TRY(cbs_fwd_trans_key_load(tk_path.c_str(), k10_9.data(), k8_1.data(), k0.data()));
     else STAGE_TRY(cbs_trans_key_load(tk_path.c_str(), k10_9.data(), k8_1.data(), k0.data()));
 
+    clk.mark("read_trans_key");
     int ngpu = 0;
     if (cbs_device_count(&ngpu) != CBS_OK || ngpu == 0) {
         fprintf(stderr, "Error: no CUDA device (this executable has no CPU fallback)\n");
@@ -50,6 +54,11 @@ int main(int argc, char **argv)
     ngpu = std::min(ngpu, nblocks);
 
     std::vector<uint64_t> result((size_t)nblocks * 128 * CBS_LWE_BIG_WORDS);
+    if (getenv("CBS_STAGE_TIMING")) {  // separate the driver / primary-context start-up from our own set-up
+        for (int g = 0; g < ngpu; g++) cbs_device_init(g);
+        clk.mark("cuda_init");
+    }
+    std::vector<double> t_ctx(ngpu, 0.0), t_run(ngpu, 0.0);
     std::vector<int> rc(ngpu, 0);
     std::vector<std::string> err(ngpu);
     std::vector<std::thread> workers;
@@ -57,7 +66,10 @@ int main(int argc, char **argv)
         workers.emplace_back([&, g]() {
             const int b0 = (int)((long)nblocks * g / ngpu), b1 = (int)((long)nblocks * (g + 1) / ngpu);
             cbs_ctx *ctx = nullptr;
+            const auto w0 = std::chrono::steady_clock::now();
             rc[g] = cbs_ctx_create(ks, g, &ctx);
+            const auto w1 = std::chrono::steady_clock::now();
+            t_ctx[g] = std::chrono::duration<double, std::milli>(w1 - w0).count();
             if (rc[g] == CBS_OK && !ctr_mode)
                 rc[g] = cbs_aes128_transcipher(ctx, ct.data() + (size_t)b0 * 16, b1 - b0, k10_9.data(), k8_1.data(), k0.data(),
                                                result.data() + (size_t)b0 * 128 * CBS_LWE_BIG_WORDS);
@@ -74,10 +86,15 @@ int main(int argc, char **argv)
                                                    k0.data(), result.data() + (size_t)b0 * 128 * CBS_LWE_BIG_WORDS);
             }
             if (rc[g] != CBS_OK) err[g] = cbs_last_error();
+            t_run[g] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w1).count();
             cbs_ctx_destroy(ctx);
         });
     }
     for (auto &w : workers) w.join();
+    clk.mark("workers");
+    clk.add("ctx_create_max", *std::max_element(t_ctx.begin(), t_ctx.end()));
+    clk.add("transcipher_max", *std::max_element(t_run.begin(), t_run.end()));
+    clk.add("gpus", ngpu);
     for (int g = 0; g < ngpu; g++)
         if (rc[g] != CBS_OK) {
             fprintf(stderr, "Error: GPU %d: %s\n", g, err[g].c_str());
@@ -85,6 +102,7 @@ int main(int argc, char **argv)
         }
     STAGE_TRY(cbs_lwe_list_save((io_dir + "/ciphertext_aes_download/result.bin").c_str(), result.data(),
                                 (uint64_t)nblocks * 128, CBS_LWE_BIG_WORDS));
+    clk.mark("write_result");
     cbs_keyset_free(ks);
     return 0;
 }

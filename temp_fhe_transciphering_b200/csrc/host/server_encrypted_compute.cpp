@@ -19,6 +19,7 @@ int main(int argc, char **argv)
 {
     long size;
     if (!parse_size(argc, argv, &size)) return 1;
+    StageClock clk("server_encrypted_compute");
     const std::string io_dir = std::string("io/") + size_string(size);
 
     uint64_t *data = nullptr, count = 0, words = 0;
@@ -34,8 +35,10 @@ int main(int argc, char **argv)
         fprintf(stderr, "Error: the inner product needs an even number of values\n");
         return 1;
     }
+    clk.mark("read_input");
     cbs_keyset *ks = nullptr;
     STAGE_TRY(cbs_keyset_load_dir(io_dir.c_str(), 0, &ks));
+    clk.mark("read_public_keys");
     int ngpu = 0;
     if (cbs_device_count(&ngpu) != CBS_OK || ngpu == 0) {
         fprintf(stderr, "Error: no CUDA device (this executable has no CPU fallback)\n");
@@ -46,12 +49,18 @@ int main(int argc, char **argv)
     ngpu = std::max(1, std::min(ngpu, units / 8));      // a shard below 8 units is not worth a context
     const size_t vw = (size_t)16 * CBS_LWE_BIG_WORDS;   // words per value
     std::vector<uint64_t> out(vw);
+    if (getenv("CBS_STAGE_TIMING")) {
+        for (int g = 0; g < ngpu; g++) cbs_device_init(g);
+        clk.mark("cuda_init");
+    }
 
     if (ngpu == 1) {
         cbs_ctx *ctx = nullptr;
         STAGE_TRY(cbs_ctx_create(ks, 0, &ctx));
+        clk.mark("ctx_create");
         if (inner) STAGE_TRY(cbs_inner_product_u16(ctx, data, nvals, out.data()));
         else STAGE_TRY(cbs_max_u16(ctx, data, nvals, out.data()));
+        clk.mark("compute");
         cbs_ctx_destroy(ctx);
     } else {
         std::vector<uint64_t> partial((size_t)ngpu * vw);
@@ -82,9 +91,12 @@ int main(int argc, char **argv)
             }
         if (inner) STAGE_TRY(cbs_sum_u16(ctxs[0], partial.data(), ngpu, out.data()));
         else STAGE_TRY(cbs_max_u16(ctxs[0], partial.data(), ngpu, out.data()));
+        clk.mark("workers_and_combine");
         for (cbs_ctx *c : ctxs) cbs_ctx_destroy(c);
     }
+    clk.add("gpus", ngpu);
     STAGE_TRY(cbs_lwe_list_save((io_dir + "/ciphertexts_download/result.bin").c_str(), out.data(), 16, CBS_LWE_BIG_WORDS));
+    clk.mark("write_result");
     cbs_keyset_free(ks);
     cbs_free(data);
     return 0;

@@ -3,7 +3,9 @@
 #pragma once
 #include "cbs_b200.h"
 
+#include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <fstream>
 #include <sstream>
@@ -55,6 +57,45 @@ inline bool read_hex_file(const std::string &path, std::vector<uint8_t> &out)
     }
     return true;
 }
+
+// Wall-clock breakdown of a stage process (the harness only records the total per stage, harness/utils.py:85-109).
+// CBS_STAGE_TIMING=1 prints one JSON line to stderr at exit, any other value appends it to that file.
+struct StageClock {
+    const char *dest = getenv("CBS_STAGE_TIMING");
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    std::string name, json;
+    explicit StageClock(const char *stage) : name(stage) {}
+    void mark(const char *what)
+    {
+        if (!dest) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof buf, "%s\"%s_ms\": %.1f", json.empty() ? "" : ", ", what,
+                 std::chrono::duration<double, std::milli>(now - last).count());
+        json += buf;
+        last = now;
+    }
+    void add(const char *what, double ms)
+    {
+        if (!dest) return;
+        char buf[96];
+        snprintf(buf, sizeof buf, "%s\"%s_ms\": %.1f", json.empty() ? "" : ", ", what, ms);
+        json += buf;
+    }
+    ~StageClock()
+    {
+        if (!dest) return;
+        char buf[96];
+        snprintf(buf, sizeof buf, ", \"total_ms\": %.1f}\n",
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        const std::string line = "{\"stage\": \"" + name + "\", " + json + buf;
+        FILE *f = strcmp(dest, "1") == 0 ? stderr : fopen(dest, "a");
+        if (f) {
+            fputs(line.c_str(), f);
+            if (f != stderr) fclose(f);
+        }
+    }
+};
 
 #define STAGE_TRY(expr)                                                   \
     do {                                                                  \

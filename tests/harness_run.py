@@ -71,6 +71,8 @@ def run(workdir, size, mini_workload=0, seed=None, servers="ours", env_extra=Non
     env["PYTHONPATH"] = SHIMS + os.pathsep + env.get("PYTHONPATH", "")
     env["CBS_MINI_WORKLOAD"] = str(mini_workload)
     env["LD_LIBRARY_PATH"] = os.path.dirname(BIN) + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    timing_file = os.path.join(workdir, "stage_timing.jsonl")
+    env.setdefault("CBS_STAGE_TIMING", timing_file)  # per-phase breakdown of OUR stage processes (stage_common.h StageClock)
     if env_extra:
         env.update(env_extra)
     cmd = ["python3", os.path.join("harness", "run_submission.py"), str(size)]
@@ -89,6 +91,8 @@ def run(workdir, size, mini_workload=0, seed=None, servers="ours", env_extra=Non
     rj = os.path.join(workdir, "measurements", name, "results.json")
     if os.path.isfile(rj):
         res["results_json"] = json.load(open(rj))
+    if os.path.isfile(timing_file):
+        res["stage_timing"] = [json.loads(l) for l in open(timing_file) if l.strip()]
     return res
 
 
@@ -98,7 +102,8 @@ def summary(res):
             "pass_aes": res["pass_aes"], "pass_result": res["pass_result"], "rc": res["rc"],
             "stage7_s": ps.get("Encrypted aes decryption"), "stage8_s": ps.get("Encrypted computation of mini workload"),
             "keygen_s": ps.get("FHE Key Generation"), "encode_s": ps.get("AES key encoding and encryption"),
-            "total_latency_s": res.get("results_json", {}).get("total_latency_s"), "wall_s": res["wall_s"]}
+            "total_latency_s": res.get("results_json", {}).get("total_latency_s"), "wall_s": res["wall_s"],
+            "stage_timing": res.get("stage_timing")}
 
 
 def main():

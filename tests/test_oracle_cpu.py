@@ -319,3 +319,33 @@ def test_max_circuit_plan(cbs):
                 v[1] = v[0] ^ 1
             assert cbs.max_plan_check(v)[0] == int(v.max()), (n, trial)
     assert [cbs.max_plan_check(np.zeros(n, np.uint16))[1:3] for n in (8, 64, 512)] == [(385, 6), (3465, 12), (28105, 18)]
+
+
+def test_unseeded_key_generation_uses_os_entropy(cbs, tmp_path):
+    """without a seed the client stages must not produce predictable keys.  Two unseeded generations differ in
+    secret key, masks and noise; the secret is balanced; a ciphertext of the unseeded key set still decrypts (phase of a
+    bootstrap-key row = -s_i * S * 2^41 up to GLWE noise); the stage executable follows the same rule."""
+    import subprocess
+    a, b = cbs.KeySet.generate(), cbs.KeySet.generate()
+    assert (a.glwe_sk != b.glwe_sk).any() and (a.lwe_sk_small != b.lwe_sk_small).any()
+    assert (a.bsk[:4096] != b.bsk[:4096]).any() and (a.ksk != b.ksk).any()
+    assert 850 < int(a.glwe_sk.sum()) < 1200 and 300 < int(a.lwe_sk_small.sum()) < 470
+    # row 2 (body row) of BSK_0 encrypts s_0 * 2^41 in the constant coefficient
+    ph = glwe_phase(a.bsk.reshape(-1, 3072)[2].reshape(1, 3072), a.glwe_sk)[0]
+    want = np.zeros(1024, dtype=np.uint64)
+    want[0] = np.uint64(int(a.lwe_sk_small[0]) << 41)
+    assert log2max(sdiff(ph, want)) < 20
+    # seeded generation stays reproducible
+    c, d = cbs.KeySet.generate(5), cbs.KeySet.generate(5)
+    assert (c.glwe_sk == d.glwe_sk).all() and (c.ksk == d.ksk).all()
+    # the executable: unseeded runs write different secret keys, CBS_SEED makes them equal
+    exe = os.path.join(ROOT, "temp_fhe_transciphering_b200", "bin", "client_key_generation")
+    env = {k: v for k, v in os.environ.items() if k != "CBS_SEED"}
+    sks = []
+    for run in ("u1", "u2", "s1", "s2"):
+        d_ = tmp_path / run
+        d_.mkdir()
+        e = dict(env, CBS_SEED="77") if run.startswith("s") else env
+        subprocess.run([exe, "0"], cwd=d_, check=True, env=e, timeout=300)
+        sks.append((d_ / "io" / "toy" / "secret_keys" / "glwe_sk.bin").read_bytes())
+    assert sks[0] != sks[1] and sks[2] == sks[3] and sks[0] != sks[2]
