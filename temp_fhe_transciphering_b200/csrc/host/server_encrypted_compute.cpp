@@ -60,8 +60,7 @@ int main(int argc, char **argv)
         clk.mark("ctx_create");
         if (inner) STAGE_TRY(cbs_inner_product_u16(ctx, data, nvals, out.data()));
         else STAGE_TRY(cbs_max_u16(ctx, data, nvals, out.data()));
-        clk.mark("compute");
-        cbs_ctx_destroy(ctx);
+        clk.mark("compute");  // one-shot process: the context is left to process exit
     } else {
         std::vector<uint64_t> partial((size_t)ngpu * vw);
         std::vector<int> rc(ngpu, 0);
@@ -92,7 +91,6 @@ int main(int argc, char **argv)
         if (inner) STAGE_TRY(cbs_sum_u16(ctxs[0], partial.data(), ngpu, out.data()));
         else STAGE_TRY(cbs_max_u16(ctxs[0], partial.data(), ngpu, out.data()));
         clk.mark("workers_and_combine");
-        for (cbs_ctx *c : ctxs) cbs_ctx_destroy(c);
     }
     clk.add("gpus", ngpu);
     STAGE_TRY(cbs_lwe_list_save((io_dir + "/ciphertexts_download/result.bin").c_str(), out.data(), 16, CBS_LWE_BIG_WORDS));

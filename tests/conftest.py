@@ -11,6 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "slow: a minute or more of GPU time (BASELINE config 5: 1024 blocks + both mini-workloads)")
 
 
 def _have_gpu():
