@@ -1183,249 +1183,13 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     }
 }
 
-// ---- trace v4: one 64-thread group per GLWE, the six keyswitch accumulators in TENSOR MEMORY ---------------------------
-// ncu r01b on k_trace_v3 (profiles/r01b_trace_ncu_full.csv): FP64 pipe 35 %, 0.69 barrier and 0.57 long-scoreboard stalls
-// per issue - two sub-groups per GLWE meet at eleven 128-thread barriers per step (spectrum exchange, serialised limb
-// updates) and the four single-slot key lanes hold exactly one digit level.  The split into two sub-groups existed only
-// because the 2 limbs x 3 columns of accumulators (192 registers) do not fit one thread.  Blackwell's tensor memory does
-// hold them: 6 x 32 words per thread, read-modify-written 4 complex values at a time with tcgen05.ld/st (SASS LDTM/STTM;
-// tools/bench_tmem.cu: 360-470 B/clk/SM, no interference with the shared-memory pipe).  So a GLWE is owned by ONE group
-// exactly like a blind-rotation accumulator: no exchange tile, no cross-group barrier, 4 GLWEs per CTA instead of 2, and
-// the key tiles (24 KB = [in poly][limb][level] x 3 columns) stream through the same 2-deep TMA ring as the BSK rows.
-__device__ __forceinline__ void tmem_alloc_cols(uint32_t *slot, int cols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_cols(uint32_t addr, int cols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// four complex doubles <-> 16 tensor-memory columns of this thread's lane; the 32-bit halves are packed / unpacked inside
-// the asm block so that ptxas coalesces them with the 64-bit registers
-__device__ __forceinline__ void tmem_ld_c4(uint32_t taddr, cplx *w)
-{
-    asm volatile(
-        "{\n\t.reg .b32 t<16>;\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%8];\n\t"
-        "tcgen05.wait::ld.sync.aligned;\n\t"
-        "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t"
-        "mov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t}"
-        : "=d"(w[0].x), "=d"(w[0].y), "=d"(w[1].x), "=d"(w[1].y), "=d"(w[2].x), "=d"(w[2].y), "=d"(w[3].x), "=d"(w[3].y)
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_c4(uint32_t taddr, const cplx *w)
-{
-    asm volatile(
-        "{\n\t.reg .b32 t<16>;\n\t"
-        "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\t"
-        "mov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\t"
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15};\n\t}" ::"r"(taddr),
-        "d"(w[0].x), "d"(w[0].y), "d"(w[1].x), "d"(w[1].y), "d"(w[2].x), "d"(w[2].y), "d"(w[3].x), "d"(w[3].y)
-        : "memory");
-}
-
-constexpr int kTr4Groups = 4;
-constexpr int kTr4GroupSmem = kGlweWords * 8 + 2 * 512 * 16;                                    // GLWE 24 KB + 2 transpose tiles
-constexpr int kTr4SmemBytes = kTr4Groups * kTr4GroupSmem + kBrRing * kBrTileBytes + 64;         // + ring + mbarriers, tmem slot
-constexpr int kTr4Tiles = 10 * 2 * 3 * 2;                                                       // (step, in poly, level, limb)
-
-__global__ void __launch_bounds__(64 * kTr4Groups, 1) k_trace_v4(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
-                                                                  int count, int from_acc, const double *__restrict__ auto_f,
-                                                                  const double *__restrict__ twtab)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6, t = threadIdx.x & 63, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * kTr4Groups + gi;
-    unsigned char *ring = smem_raw + (size_t)kTr4Groups * kTr4GroupSmem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes);
-    uint64_t *empty = full + kBrRing;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + kBrRing);
-    const int active_groups = min(kTr4Groups, count - blockIdx.x * kTr4Groups);
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < kBrRing; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, 2 * active_groups);  // one arrive per warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tmem_alloc_cols(tmem_slot, 512);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // a warp reaches lane quarter warp % 4 of tensor memory only; the two warps of a quarter take 256 columns each:
-    // accumulator (limb, column c) of this thread at columns 32 * (3 limb + c) .. + 31
-    const uint32_t tm = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(256 * (warp >> 2));
-    if (idx < count) {
-        const bool producer = (threadIdx.x == 0);
-        const char *key_bytes = reinterpret_cast<const char *>(auto_f);
-        // tile n = ((step * 2 + in poly) * 3 + tt) * 2 + limb, digit level lev = 2 - tt: Fourier polys [s][i][limb][lev][0..2]
-        auto tile_src = [&](int n) {
-            const int limb = n & 1, tt = (n >> 1) % 3, si = n / 6;
-            return key_bytes + (size_t)(((si * 2 + limb) * 3 + (2 - tt)) * 3) * kFourierPolyDoubles * 8;
-        };
-        if (producer)
-            for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, tile_src(b), kBrTileBytes, full + b);
-        __syncwarp();
-        unsigned char *base = smem_raw + (size_t)gi * kTr4GroupSmem;
-        u64x2 *cur = reinterpret_cast<u64x2 *>(base);  // [3][512] pairs (coef j, coef j + 512)
-        cplx *scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
-        cplx *scr1 = scr0 + 512;
-        int flip = 0;
-        const int bar = 1 + gi;
-        Twiddles tw;
-        load_twiddles_x(tw, twtab, t);
-        if (from_acc) {  // ggsw_conv.rs:302-314 fused into the load
-            const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
-            const int lvl = idx % kCbsLevel;
-            for (int w = t; w < 3 * 512; w += 64) {
-                const int p = w >> 9, jj = w & 511;
-                cur[w] = u64x2{glev_pre_word(acc, lvl, p, jj), glev_pre_word(acc, lvl, p, jj + 512)};
-            }
-        } else {
-            const uint64_t *src = in + (size_t)idx * kGlweWords;
-            for (int w = t; w < 3 * 512; w += 64) {
-                const int p = w >> 9, jj = w & 511;
-                cur[w] = u64x2{src[p * 1024 + jj], src[p * 1024 + jj + 512]};
-            }
-        }
-        group_sync(bar);
-
-        int tile = 0;
-#pragma unroll 1
-        for (int s = 0; s < 10; s++) {
-            const int kinv = c_kappa_inv[s];
-            // body: out.body = in.body + in.body(X^kappa) (+ the keyswitch's body column, added below); all permuted reads
-            // of the body happen before its first write (automorphism.rs:225-229, utils.rs:475-490)
-            {
-                u64x2 nb[8];
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const int jj = t + 64 * m;
-                    const int e = (jj * kinv) & 2047;
-                    const u64x2 A = cur[1024 + (e & 511)];
-                    const int h = e >> 9;
-                    const u64x2 own = cur[1024 + jj];
-                    nb[m] = u64x2{own.lo + pair_pick(A, h), own.hi + pair_pick(A, (h + kinv) & 3)};
-                }
-                group_sync(bar);
-#pragma unroll
-                for (int m = 0; m < 8; m++) cur[1024 + t + 64 * m] = nb[m];
-            }
-            // forward: the mask polynomials are only read here and only written in the update phase below
-#pragma unroll 1
-            for (int i = 0; i < 2; i++) {
-                uint64_t pk[16];
-                {
-                    const u64x2 *p = cur + i * 512;
-#pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        const int jj = t + 64 * m;
-                        const int e = (jj * kinv) & 2047;
-                        const u64x2 A = p[e & 511];
-                        const int h = e >> 9;
-                        pk[2 * m] = pack_digits<13, 3, uint64_t>(pair_pick(A, h));
-                        pk[2 * m + 1] = pack_digits<13, 3, uint64_t>(pair_pick(A, (h + kinv) & 3));
-                    }
-                }
-#pragma unroll 1
-                for (int tt = 0; tt < 3; tt++) {
-                    cplx v[8];
-#pragma unroll
-                    for (int m = 0; m < 8; m++)
-                        v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m], tt)),
-                                    i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m + 1], tt))};
-                    cplx *sc = flip ? scr1 : scr0;
-                    flip ^= 1;
-                    fwd_p1(v, sc, tw, t);
-                    group_sync(bar);
-                    fwd_p2x(v, sc, tw, t);
-                    exchange8<-1>(v, t & 7);
-                    fwd_p3x(v);
-                    const bool first = (i == 0 && tt == 0);
-#pragma unroll 1
-                    for (int limb = 0; limb < 2; limb++, tile++) {
-                        const int buf = tile % kBrRing, use = tile / kBrRing;
-                        if (producer && tile >= 1 && tile - 1 + kBrRing < kTr4Tiles) {
-                            const int pb = (tile - 1) % kBrRing, puse = (tile - 1) / kBrRing;
-                            mbar_wait(empty + pb, puse & 1);
-                            tma_load_tile(ring + pb * kBrTileBytes, tile_src(tile - 1 + kBrRing), kBrTileBytes, full + pb);
-                        }
-                        __syncwarp();
-                        mbar_wait(full + buf, use & 1);
-                        const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-#pragma unroll
-                            for (int hh = 0; hh < 2; hh++) {
-                                const uint32_t col = tm + 32 * (3 * limb + c) + 16 * hh;
-                                cplx w[4];
-                                if (first) {
-#pragma unroll
-                                    for (int k = 0; k < 4; k++) w[k] = cmul(v[4 * hh + k], key[c * 512 + (4 * hh + k) * 64]);
-                                } else {
-                                    tmem_ld_c4(col, w);
-#pragma unroll
-                                    for (int k = 0; k < 4; k++) cfma(w[k], v[4 * hh + k], key[c * 512 + (4 * hh + k) * 64]);
-                                }
-                                tmem_st_c4(col, w);
-                            }
-                        }
-                        __syncwarp();  // every lane's tile reads have been consumed
-                        if (lane == 0) mbar_arrive(empty + buf);
-                    }
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // before the next spectrum reads the sums back
-                }
-            }
-            // inverse + update: column c += lo limb + (hi limb << 41)  (fourier_glwe_keyswitch.rs:323-341)
-#pragma unroll 1
-            for (int c = 0; c < 3; c++) {
-                uint64_t rl[8], rh[8];
-#pragma unroll 1
-                for (int limb = 0; limb < 2; limb++) {
-                    cplx a[8];
-                    tmem_ld_c4(tm + 32 * (3 * limb + c), a);
-                    tmem_ld_c4(tm + 32 * (3 * limb + c) + 16, a + 4);
-                    cplx *sc = flip ? scr1 : scr0;
-                    flip ^= 1;
-                    inv_p3x(a);
-                    exchange8<1>(a, t & 7);
-                    inv_p2x(a, sc, tw, t);
-                    group_sync(bar);
-                    inv_p1(a, sc, tw, t);
-                    const int shift = limb ? 41 : 0;
-#pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        const uint64_t x = torus_from_scaled(a[m].x) << shift, y = torus_from_scaled(a[m].y) << shift;
-                        rl[m] = limb ? rl[m] + x : x;
-                        rh[m] = limb ? rh[m] + y : y;
-                    }
-                }
-                u64x2 *p = cur + c * 512;
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    u64x2 w = p[t + 64 * m];
-                    w.lo += rl[m];
-                    w.hi += rh[m];
-                    p[t + 64 * m] = w;
-                }
-            }
-            group_sync(bar);  // the GLWE is complete before the next step's permuted reads
-        }
-        uint64_t *dst = out + (size_t)idx * kGlweWords;
-        for (int w = t; w < 3 * 512; w += 64) {
-            const u64x2 x = cur[w];
-            const int c = w >> 9, jj = w & 511;
-            dst[c * 1024 + jj] = x.lo;
-            dst[c * 1024 + jj + 512] = x.hi;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 512);
-}
-
+// Round 2, measured and rejected (code in git history, "trace v4"): one 64-thread group per GLWE with the six keyswitch
+// accumulators in TENSOR MEMORY (tcgen05.ld/st, one round trip per accumulator and input polynomial, the three digit
+// spectra resident in registers, key tiles regrouped per (in poly, limb, column) as three 8 KB bulk copies on one
+// mbarrier): no exchange tile, no cross-group barrier, 4 GLWEs per CTA - parity-green, and the same throughput per SM as
+// this kernel (0.243 ms per wave of 592 GLWEs against 2 x 0.116 ms per wave of 296; profiles/r02_brbench_variants.txt).
+// Like the blind rotation the trace is not limited by its barriers but by three co-limiting pipes (FP64 35 %, shared
+// memory 59 %, issue 39 %) at 8 warps per SM, which the register file (255 per thread) and shared memory pin.
 void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int count, int from_acc, cudaStream_t s)
 {
     if (count <= 0) return;
@@ -1444,18 +1208,9 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
         }
         cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
         cudaFuncSetAttribute(k_trace_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
-        cudaFuncSetAttribute(k_trace_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr4SmemBytes);
         init = true;
     }
-    static const int variant = [] {
-        const char *e = getenv("CBS_TRACE_VARIANT");
-        return e ? atoi(e) : 4;
-    }();
-    if (variant == 3)
-        k_trace_v3<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc, K.auto_f, K.tw);
-    else
-        k_trace_v4<<<(count + kTr4Groups - 1) / kTr4Groups, 64 * kTr4Groups, kTr4SmemBytes, s>>>(in, out, count, from_acc, K.auto_f,
-                                                                                               K.tw);
+    k_trace_v3<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc, K.auto_f, K.tw);
 }
 
 // ------------------------------------------------------------------------------------------------
