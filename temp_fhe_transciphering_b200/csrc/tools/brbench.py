@@ -35,5 +35,5 @@ def timed(fn, reps=5):
 
 br = timed(lambda: ctx.blind_rotate_dev(small.data_ptr(), acc.data_ptr(), B))
 cb = timed(lambda: ctx.circuit_bootstrap_dev(small.data_ptr(), B))
-print("BR_VARIANT", os.environ.get("CBS_BR_VARIANT"), "TRACE_VARIANT", os.environ.get("CBS_TRACE_VARIANT"), "B", B,
+print("B", B,
       "blind_rotate_ms %.3f" % br, "circuit_bootstrap_ms %.3f" % cb, "trace+ss_ms %.3f" % (cb - br))
