@@ -5,12 +5,16 @@
   python bench.py --impl reference --gpus N --steps K ...   (the reference's own CPU path, rank 0 only)
 
 A step = one pass of the hot path (aes_to_lwe_trasnciphering, stage 7 of the reference) over one
-batch of synthetic AES blocks: BLOCKS_PER_GPU = 8 blocks per GPU = the "small instance (size 1)"
-of BASELINE.json configs[1] (64 u16 values); at N GPUs every rank transciphers its own 8 blocks
-(weak scaling; N = 8 is the medium instance, 64 blocks).  Inputs: seeded FHE keys (binary secrets,
-AES_TIGHT Gaussian noise), AES key sha256("None")[:16] as in the harness, ECB blocks (the mode the
-reference implements).  After the timed region the last result is decrypted with the secret key and
-compared with the plaintext ("verified").
+batch of synthetic AES blocks: BLOCKS_PER_GPU = 8 blocks per GPU = the block count of the small
+instance (BASELINE.json configs[1], 64 u16 values); at N GPUs every rank transciphers its own 8
+blocks (weak scaling; N = 8 is the block count of the medium instance, 64).  The headline leg runs
+ECB block DECRYPTION, the one mode the reference's stage 7 implements (so the reference arm times the
+same operation); the harness encrypts sizes 1/2 in CTR mode (harness/aes_keygen_and_encrypt.py:49-55),
+which needs forward AES on the counters - that path (cbs_aes128_ctr_transcipher_dev, what our stage 7
+runs for sizes 1/2) is timed on the same 8 blocks and reported under "ctr".  Inputs: seeded FHE keys
+(binary secrets, AES_TIGHT Gaussian noise), AES key sha256("None")[:16] as in the harness.  After the
+timed region the last result is decrypted with the secret key and compared with the plaintext
+("verified"; AES_TIGHT itself leaves ~0.05 % of blocks wrong).
 """
 import argparse
 import json
@@ -30,13 +34,14 @@ CBS_PER_BLOCK = 1152           # 9 bootstrapped rounds x 128 state bits (SURVEY.
 BR_MFLOP = 148.6               # FP64 MFLOP per blind rotation
 BSK_BYTES = 56_623_104         # Fourier bootstrapping key streamed once per launch
 BR_IO_BYTES = 30_728           # LWE in + accumulator out per blind rotation
+NCU_BR_CSV = "r02_blind_rotate_ncu_full.csv"   # ncu --set full of k_blind_rotate_v3 on the 512-ciphertext lane shape the step launches
 METRIC = "AES-128 blocks transciphered/sec"
 UNIT = "blocks/s"
 
 
 def read_ncu_traffic():
     """DRAM bytes per blind-rotation launch from the committed ncu --set full capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r01b_blind_rotate_ncu_full.csv")
+    p = os.path.join(ROOT, "profiles", NCU_BR_CSV)
     try:
         rd = wr = None
         for line in open(p):
@@ -52,7 +57,7 @@ def read_ncu_traffic():
 
 def read_ncu_metric(name):
     """One metric of the throughput blind-rotation kernel from the committed ncu --set full summary (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r01b_blind_rotate_ncu_full.csv")
+    p = os.path.join(ROOT, "profiles", NCU_BR_CSV)
     try:
         for line in open(p):
             f = line.strip().split(",")
@@ -125,31 +130,41 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm: the reference's own prebuilt, unmodified stage-7 binary on the host cores
 def make_reference_workdirs(base, copies):
-    """io/ + datasets/ for the toy instance (1 block, ECB), written by OUR seeded client helpers in the
-    reference's bincode formats; one cwd per concurrent copy, sharing the read-only inputs."""
+    """io/ + datasets/ for the toy instance (1 block, ECB).  Keys and transciphering key come from the REFERENCE's own
+    prebuilt client binaries (oracle/_ref/client_key_generation, client_encode_encrypt), the AES ciphertext from the
+    pure-Python oracle/aes_clear.py: nothing of this repository's library is loaded by the reference arm.
+    One cwd per concurrent copy, sharing the read-only inputs."""
     import numpy as np
-    import temp_fhe_transciphering_b200 as cbs
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import aes_clear
+    ref = os.path.join(ROOT, "oracle", "_ref")
     shared = os.path.join(base, "shared")
-    ks = cbs.KeySet.generate(777)
     aes_key = aes_clear.harness_aes_key(None)
-    pt = bytes(np.random.default_rng(5).integers(0, 256, 16, dtype=np.uint8))
-    ct = aes_clear.ecb_encrypt(aes_key, pt)
-    ks.save_dir(os.path.join(shared, "io", "toy"), with_secret=True)
-    cbs.save_trans_key(os.path.join(shared, "io", "toy", "ciphertexts_upload", "trans_key.bin"),
-                       *ks.gen_transciphering_keys(aes_key, 778))
+    vals = np.random.default_rng(5).integers(0, 65536, 8).tolist()
+    ct = aes_clear.ecb_encrypt(aes_key, aes_clear.pack_u16_be(vals))
     os.makedirs(os.path.join(shared, "datasets", "toy"), exist_ok=True)
+    open(os.path.join(shared, "datasets", "toy", "aes_key.hex"), "w").write(aes_key.hex())
     open(os.path.join(shared, "datasets", "toy", "db.hex"), "w").write(ct.hex())
+    for exe in ("client_key_generation", "client_encode_encrypt"):
+        subprocess.run([os.path.join(ref, exe), "0"], cwd=shared, check=True, stdout=subprocess.DEVNULL)
     dirs = []
     for c in range(copies):
         d = os.path.join(base, f"copy{c}")
         os.makedirs(os.path.join(d, "io", "toy"))
         os.symlink(os.path.join(shared, "datasets"), os.path.join(d, "datasets"))
-        for sub in ("public_keys", "ciphertexts_upload"):
+        for sub in ("public_keys", "ciphertexts_upload", "secret_keys"):
             os.symlink(os.path.join(shared, "io", "toy", sub), os.path.join(d, "io", "toy", sub))
         dirs.append(d)
-    return dirs, ks, pt
+    return dirs, vals
+
+
+def reference_decrypts_to(d, vals):
+    """decrypt stage 7's result.bin with the reference's own client binaries and compare with the expected values."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    for exe in ("client_decrypt_decode_aes_decryption", "client_postprocess_aes_decryption"):
+        subprocess.run([os.path.join(ref, exe), "0"], cwd=d, check=True, stdout=subprocess.DEVNULL)
+    got = [int(x) for x in open(os.path.join(d, "io", "toy", "result_aes.txt")).read().split()]
+    return got == vals
 
 
 def run_reference_wave(dirs, binary):
@@ -168,13 +183,9 @@ def reference_blocks_per_s(copies, waves):
     base = tempfile.mkdtemp(prefix="cbs_ref_")
     try:
         if os.path.exists(binary):
-            dirs, ks, pt = make_reference_workdirs(base, copies)
+            dirs, vals = make_reference_workdirs(base, copies)
             times = [run_reference_wave(dirs, binary) for _ in range(waves)]
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import numpy as np
-            import ref_io
-            out = ref_io.read_lwe_list(os.path.join(dirs[0], "io", "toy", "ciphertext_aes_download", "result.bin"))
-            ok = np.packbits(ref_io.decode_bit(ref_io.lwe_phase(out, ks.glwe_sk))).tobytes() == pt
+            ok = reference_decrypts_to(dirs[0], vals)
             t = sum(times) / len(times)
             return copies / t, t, "reference", bool(ok)
         # fallback: the C oracle port (OpenMP over all host threads), one block per "wave"
@@ -325,8 +336,34 @@ def main_ours(args):
     ms_total = float(ms.item())
     value = world * nblocks * args.steps / (ms_total * 1e-3)
 
+    # --- CTR leg: the mode the harness uses for sizes 1/2 (forward AES of the public counters, 3 LUT multiples per byte,
+    #     forward linear layer, XOR with the ciphertext bits); same blocks, device-resident, same timing rules ---
+    iv = aes_clear.harness_iv(None)
+    ctr_ct = aes_clear.ctr_crypt(aes_key, iv, pt)
+    ctx.upload_fwd_trans_key(*ks.gen_forward_transciphering_keys(aes_key, 31338))
+    counters = b"".join(((int.from_bytes(iv, "big") + b) % (1 << 128)).to_bytes(16, "big") for b in range(nblocks))
+    d_ctr = torch.frombuffer(bytearray(counters), dtype=torch.uint8).cuda()
+    d_cct = torch.frombuffer(bytearray(ctr_ct), dtype=torch.uint8).cuda()
+    d_cout = torch.empty((nblocks, 128, 2049), dtype=torch.int64, device="cuda")
+    ctr_steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 3)):
+        ctx.ctr_transcipher_dev(d_ctr.data_ptr(), d_cct.data_ptr(), nblocks, d_cout.data_ptr())
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(stream)
+    for _ in range(ctr_steps):
+        ctx.ctr_transcipher_dev(d_ctr.data_ptr(), d_cct.data_ptr(), nblocks, d_cout.data_ptr())
+    c1.record(stream)
+    barrier()
+    cms = torch.tensor([c0.elapsed_time(c1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+    ctr_value = world * nblocks * ctr_steps / (float(cms.item()) * 1e-3)
+
     # verify the last device-resident result (untimed)
     import ref_io
+    ctr_ok = np.packbits(ref_io.decode_bit(ref_io.lwe_phase(d_cout.cpu().numpy().view(np.uint64).reshape(-1, 2049),
+                                                            ks.glwe_sk))).tobytes() == pt
     out = d_out.cpu().numpy().view(np.uint64)
     bits, std, mx = ref_io.noise_stats(out.reshape(-1, 2049), ks.glwe_sk)
     verified = np.packbits(bits).tobytes() == pt
@@ -408,9 +445,10 @@ def main_ours(args):
         achieved = BR_MFLOP * 1e6 * B / (br_ms * 1e-3) * 1e-12
         br_bytes = BSK_BYTES + B * BR_IO_BYTES
         roof = {
-            "kernel": "k_blind_rotate", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "kernel": "k_blind_rotate_v3", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved / fp64_peak, "traffic": read_ncu_traffic(),
-            "traffic_source": "profiles/r01b_blind_rotate_ncu_full.csv (ncu --set full, same kernel, 1024 ciphertexts)", "peak_source": "FP64 FMA probe kernel, same run",
+            "traffic_source": f"profiles/{NCU_BR_CSV} (ncu --set full, same kernel, same 512-ciphertext launch shape)",
+            "peak_source": "FP64 FMA probe kernel, same run",
             # why frac cannot reach 1: the FMA probe counts 2 flop per issue slot, the transform mixes DADD/DMUL (1 flop)
             # with DFMA (2): 148.6 MFLOP per blind rotation are ~98.3 M FP64 instructions, so a saturated FP64 pipe would
             # read frac = 0.755; ncu's pipe-active figure of the same kernel (profiles/) is the like-for-like utilisation
@@ -420,7 +458,7 @@ def main_ours(args):
             "launch_ms": br_ms, "ciphertexts_per_launch": B, "launches_per_step": 9 * lanes,
             "share_of_step": br_ms * 9 * lanes / (ms_total / args.steps),
             "share_note": "lanes overlap on the device, so kernel shares of the step sum to more than 1; "
-                          "ncu's serialised launch list (profiles/r01b_launch_summary.csv) gives 71.5 %",
+                          "ncu's serialised launch list (profiles/r02_launch_summary.csv) gives the share of the serialised sum",
             "hbm": {"bound": "hbm", "achieved": br_bytes / (br_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": br_bytes / (br_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src + " MEASURED_PEAKS.json",
                     "algorithmic_bytes_per_launch": br_bytes},
@@ -437,14 +475,17 @@ def main_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"small instance (size 1): {nblocks} AES-128 ECB blocks per GPU = {nblocks * 128} "
-                                   f"bit-ciphertexts x 9 bootstrapped rounds, AES_TIGHT",
+            "config": {"workload": f"{nblocks} AES-128 ECB blocks per GPU (the block count of the small instance, size 1) = "
+                                   f"{nblocks * 128} bit-ciphertexts x 9 bootstrapped rounds, AES_TIGHT; CTR mode of the same "
+                                   f"blocks under 'ctr'",
                        "blocks_per_gpu": nblocks, "parallelism": f"blocks sharded over {world} GPU(s), replicated keys, "
                                                                    "no collective in the data path",
                        "l2": "per-step working set ~0.7 GB (Fourier GGSW 528 MB) exceeds the 126 MB L2"},
             "circuit_bootstraps_per_s": value * CBS_PER_BLOCK,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "verified": bool(e2e_ok)},
+            "ctr": {"value": ctr_value, "unit": UNIT, "ms_per_step": float(cms.item()) / ctr_steps, "steps": ctr_steps,
+                    "verified": bool(ctr_ok), "what": "cbs_aes128_ctr_transcipher_dev on the same blocks (harness sizes 1/2 mode)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "verified": bool(verified), "output_noise_log2_std": std, "output_noise_log2_max": mx,

@@ -447,6 +447,16 @@ class Context:
         d, p3 = _u64(k0)
         _check(lib().cbs_trans_key_upload(self._h, p1, p2, p3), "cbs_trans_key_upload")
 
+    def upload_fwd_trans_key(self, kf_first, kf_mid, kf_last):
+        """forward-direction (CTR) transciphering key -> device, once; then ctr_transcipher_dev can be called repeatedly."""
+        (a, pa), (b, pb), (c, pc) = _u64(kf_first), _u64(kf_mid), _u64(kf_last)
+        _check(lib().cbs_fwd_trans_key_upload(self._h, pa, pb, pc), "cbs_fwd_trans_key_upload")
+
+    def ctr_transcipher_dev(self, d_ctr_ptr, d_ct_ptr, nblocks, d_out_ptr):
+        """device-resident CTR transciphering: d_ctr = the public 16-byte counter blocks, d_ct = the AES-CTR ciphertext."""
+        _check(lib().cbs_aes128_ctr_transcipher_dev(self._h, ctypes.c_void_p(d_ctr_ptr), ctypes.c_void_p(d_ct_ptr), nblocks,
+                                                    ctypes.c_void_p(d_out_ptr)), "cbs_aes128_ctr_transcipher_dev")
+
     def transcipher_dev(self, d_ct_ptr, nblocks, d_out_ptr):
         _check(lib().cbs_aes128_transcipher_dev(self._h, ctypes.c_void_p(d_ct_ptr), int(nblocks), ctypes.c_void_p(d_out_ptr)),
                "cbs_aes128_transcipher_dev")
