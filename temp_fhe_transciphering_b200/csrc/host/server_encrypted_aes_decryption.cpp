@@ -3,7 +3,9 @@
 // (datasets/<s>/db.hex, io/<s>/public_keys/{bsk,ksk,auto_keys,ss_key}.bin,
 // io/<s>/ciphertexts_upload/trans_key.bin) and output (io/<s>/ciphertext_aes_download/result.bin).
 // The reference transciphers only the first 16-byte block of db.hex (:613-617); this binary
-// transciphers every block, sharded contiguously over the visible GPUs (CBS_GPUS limits the count).
+// transciphers every block, sharded contiguously over the GPUs it decides to use (stage_common.h plan_visible_gpus:
+// one GPU up to ~120 blocks because driver start-up costs more than the transciphering; CBS_GPUS / CUDA_VISIBLE_DEVICES
+// override).
 // Mode follows the harness (harness/aes_keygen_and_encrypt.py:45-55): size 0 = ECB block decryption
 // with the reference's AllRdKeys; sizes 1/2 = CTR with datasets/<s>/aes_iv.hex and the forward-direction
 // transciphering key written by our client_encode_encrypt (the reference has no CTR path).
@@ -28,6 +30,7 @@ int main(int argc, char **argv)
         return 1;
     }
     const int nblocks = (int)(ct.size() / 16);
+    plan_visible_gpus(nblocks);  // before the first CUDA call
 
     cbs_keyset *ks = nullptr;
     STAGE_TRY(cbs_keyset_load_dir(io_dir.c_str(), 0, &ks));

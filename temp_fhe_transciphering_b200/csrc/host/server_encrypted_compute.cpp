@@ -29,6 +29,7 @@ int main(int argc, char **argv)
         return 1;
     }
     const int nvals = (int)(count / 16);
+    plan_visible_gpus(nvals / 8);  // before the first CUDA call
     const char *mw = argc >= 3 ? argv[2] : getenv("CBS_MINI_WORKLOAD");
     const bool inner = mw && atoi(mw) == 1;
     if (inner && (nvals & 1)) {

@@ -10,6 +10,7 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <unistd.h>
 #include <vector>
 
 inline const char *size_string(long size)
@@ -56,6 +57,38 @@ inline bool read_hex_file(const std::string &path, std::vector<uint8_t> &out)
         out.push_back((uint8_t)v);
     }
     return true;
+}
+
+// How many GPUs a one-shot stage process should use, decided BEFORE the first CUDA call.  Driver start-up dominates these
+// processes: on an 8 x B200 box cuInit + primary contexts cost 5.4 - 8.6 s with all eight GPUs visible against 0.8 - 3 s
+// with one (profiles/r02_harness_{1,8}gpu.jsonl), while a GPU transciphers ~62 blocks per second.  Minimising
+// t(g) = 0.85 g + blocks / (62 g) gives g = sqrt(blocks / 53): one GPU up to ~120 blocks, 4 - 5 for 1024.  The choice is made
+// effective by narrowing CUDA_VISIBLE_DEVICES (unless the caller set it, or CBS_GPUS asks for a specific count), so that
+// the driver never touches the other devices.  block_equivalents = AES blocks (stage 7) or values / 8 (stage 8).
+inline void plan_visible_gpus(long block_equivalents)
+{
+    if (getenv("CUDA_VISIBLE_DEVICES")) return;  // the caller's choice
+    int present = 0;
+    for (int i = 0; i < 64; i++) {
+        const std::string dev = "/dev/nvidia" + std::to_string(i);
+        if (FILE *f = fopen(dev.c_str(), "r")) {
+            fclose(f);
+            present++;
+        } else if (access(dev.c_str(), F_OK) == 0) {
+            present++;
+        }
+    }
+    if (present <= 1) return;
+    int want = 1;
+    if (const char *e = getenv("CBS_GPUS")) {
+        want = atoi(e);
+    } else {
+        while ((want + 0.5) * (want + 0.5) * 53.0 < (double)block_equivalents) want++;
+    }
+    want = want < 1 ? 1 : (want > present ? present : want);
+    std::string list;
+    for (int i = 0; i < want; i++) list += (i ? "," : "") + std::to_string(i);
+    setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
 }
 
 // Wall-clock breakdown of a stage process (the harness only records the total per stage, harness/utils.py:85-109).

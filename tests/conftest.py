@@ -98,3 +98,34 @@ def glwe_phase(glwe, glwe_sk):
                 rolled[:, :i] = np.uint64(0) - rolled[:, :i]
                 out -= rolled
     return out
+
+
+class NoiseFailure(AssertionError):
+    """A transciphered block decrypted wrongly while the rest of the run is right: the signature of AES_TIGHT's own
+    decryption-failure probability (about one block in a thousand: heavy-tailed noise at the round inputs, see
+    profiles/r02_bigcheck.txt and DESIGN.md section 2), not of a defect - a defect is deterministic, this is not."""
+
+
+def retry_on_noise(fn, attempts=3):
+    """Run fn(attempt) until it does not raise NoiseFailure (fresh FHE keys every time); at most `attempts` times."""
+    last = None
+    for k in range(attempts):
+        try:
+            return fn(k)
+        except NoiseFailure as e:  # noqa: PERF203
+            last = e
+            print(f"[noise retry {k + 1}/{attempts}] {e}")
+    raise last
+
+
+def check_blocks(got, want, values_per_block=8, max_bad_fraction=0.25):
+    """Compare decrypted u16 values with the expectation: equal -> ok; a few whole blocks wrong -> NoiseFailure (retry);
+    anything else (length, most blocks wrong) -> plain AssertionError."""
+    assert len(got) == len(want), (len(got), len(want))
+    bad = sorted({i // values_per_block for i in range(len(want)) if got[i] != want[i]})
+    nblocks = max(1, len(want) // values_per_block)
+    if not bad:
+        return
+    if len(bad) <= max(1, int(nblocks * max_bad_fraction)):
+        raise NoiseFailure(f"{len(bad)} of {nblocks} blocks decrypt wrongly: {bad[:8]}")
+    raise AssertionError(f"{len(bad)} of {nblocks} blocks wrong: {bad[:16]}")
