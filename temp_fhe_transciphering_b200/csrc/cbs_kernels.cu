@@ -665,6 +665,286 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uin
     }
 }
 
+// ---- v6 (experimental, CBS_BR_VARIANT=64/65): v3 with the per-thread twiddles in tensor memory --------------------------
+__device__ __forceinline__ void tmem_alloc_cols(uint32_t *slot, int cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cols(uint32_t addr, int cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_c4(uint32_t taddr, cplx *w)
+{
+    asm volatile(
+        "{\n\t.reg .b32 t<16>;\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n\t"
+        "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t"
+        "mov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t}"
+        : "=d"(w[0].x), "=d"(w[0].y), "=d"(w[1].x), "=d"(w[1].y), "=d"(w[2].x), "=d"(w[2].y), "=d"(w[3].x), "=d"(w[3].y)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_c4(uint32_t taddr, const cplx *w)
+{
+    asm volatile(
+        "{\n\t.reg .b32 t<16>;\n\t"
+        "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\t"
+        "mov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\t"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15};\n\t}" ::"r"(taddr),
+        "d"(w[0].x), "d"(w[0].y), "d"(w[1].x), "d"(w[1].y), "d"(w[2].x), "d"(w[2].y), "d"(w[3].x), "d"(w[3].y)
+        : "memory");
+}
+// tm = this thread's 64 tensor-memory columns: t1x[0..7] at [0, 32), t2x[0..7] at [32, 64)
+__device__ __forceinline__ void fwd_p1_tm(cplx v[8], cplx *scr, uint32_t tm, int t)
+{
+    const double cr[8] = CBS_CM_RE, ci[8] = CBS_CM_IM;
+#pragma unroll
+    for (int m = 1; m < 8; m++) v[m] = cmul(v[m], cplx{cr[m], ci[m]});
+    dft8<false>(v);
+    const int a = t & 7, b = t >> 3;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        cplx w[4];
+        tmem_ld_c4(tm + 16 * h, w);
+#pragma unroll
+        for (int k = 0; k < 4; k++) scr[slot(4 * h + k, a, b)] = cmul(v[4 * h + k], w[k]);
+    }
+}
+__device__ __forceinline__ void fwd_p2x_tm(cplx v[8], const cplx *scr, uint32_t tm, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) v[mp] = scr[slot(k1, tp, mp)];
+    dft8<false>(v);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        cplx w[4];
+        tmem_ld_c4(tm + 32 + 16 * h, w);
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[4 * h + k] = cmul(v[4 * h + k], w[k]);
+    }
+}
+__device__ __forceinline__ void inv_p2x_tm(cplx v[8], cplx *scr, uint32_t tm, int t)
+{
+    const int k1 = t >> 3, tp = t & 7;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        cplx w[4];
+        tmem_ld_c4(tm + 32 + 16 * h, w);
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[4 * h + k] = cmul_conj(v[4 * h + k], w[k]);
+    }
+    dft8<true>(v);
+#pragma unroll
+    for (int mp = 0; mp < 8; mp++) scr[slot(k1, tp, mp)] = v[mp];
+}
+__device__ __forceinline__ void inv_p1_tm(cplx v[8], const cplx *scr, uint32_t tm, int t)
+{
+    const double cr[8] = CBS_CM_RE, ci[8] = CBS_CM_IM;
+    const int a = t & 7, b = t >> 3;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        cplx w[4];
+        tmem_ld_c4(tm + 16 * h, w);
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[4 * h + k] = cmul_conj(scr[slot(4 * h + k, a, b)], w[k]);
+    }
+    dft8<true>(v);
+#pragma unroll
+    for (int m = 1; m < 8; m++) v[m] = cmul_conj(v[m], cplx{cr[m], ci[m]});
+}
+
+template <int G, int TILES>
+struct Br6 {
+    static constexpr int kGroupSmem = kGlweWords * 8 + TILES * 8192;
+    static constexpr int kRingOff = G * kGroupSmem;
+    static constexpr int kBarOff = kRingOff + kBrRing * kBrTileBytes;
+    static constexpr int kRotOff = kBarOff + 64;
+    static constexpr int kSmemBytes = kRotOff + G * kLweN * 2;
+};
+
+template <int G, int TILES, bool PRE>
+__global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v6(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out, int count,
+                                                                const double *__restrict__ bsk_f, const double *__restrict__ twtab)
+{
+    using L = Br6<G, TILES>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gi = threadIdx.x >> 6, warp = threadIdx.x >> 5;
+    const int ct = blockIdx.x * G + gi;
+    unsigned char *ring = smem_raw + L::kRingOff;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L::kBarOff);
+    uint64_t *empty = full + kBrRing;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + kBrRing);
+    const int active_groups = min(G, count - blockIdx.x * G);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kBrRing; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, 64 * active_groups);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc_cols(tmem_slot, 256);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
+    const int t = threadIdx.x & 63;
+    {
+        Twiddles tw;
+        load_twiddles_x(tw, twtab, t);
+        tmem_st_c4(tm, tw.t1);
+        tmem_st_c4(tm + 16, tw.t1 + 4);
+        tmem_st_c4(tm + 32, tw.t2);
+        tmem_st_c4(tm + 48, tw.t2 + 4);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    if (ct < count) {
+        const bool producer = (threadIdx.x == 0);
+        const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
+        constexpr int kTiles = kLweN * 3;
+        if (producer)
+            for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
+        __syncwarp();
+        unsigned char *base = smem_raw + (size_t)gi * L::kGroupSmem;
+        u64x2 *acc = reinterpret_cast<u64x2 *>(base);
+        const int bar = 1 + gi, bar_war = 1 + G + gi;
+        cplx *scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
+        cplx *scr1 = scr0 + (TILES == 2 ? 512 : 0);
+        int flip = 0;
+        const uint64_t *a = lwe + (size_t)ct * kLweSmall;
+        uint16_t *rot = reinterpret_cast<uint16_t *>(smem_raw + L::kRotOff) + gi * kLweN;
+        for (int q = t; q < kLweN; q += 64) rot[q] = (uint16_t)(modswitch_dev(a[q]) & 2047);
+        {
+            const int bt = modswitch_dev(a[kLweN]);
+            for (int jj = t; jj < 512; jj += 64) {
+                acc[jj] = u64x2{0, 0};
+                acc[512 + jj] = u64x2{0, 0};
+                u64x2 b;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int j = jj + 512 * h;
+                    const int e = (j + bt) & 2047;
+                    const int i = e & 1023;
+                    uint64_t val = 1ull << (61 - 2 * (i & 7));
+                    const bool neg = (i < 512) != ((e & 1024) != 0);
+                    (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
+                }
+                acc[1024 + jj] = b;
+            }
+        }
+        group_sync(bar);
+        int tile = 0;
+#pragma unroll 1
+        for (int i = 0; i < kLweN; i++) {
+            const int d = rot[i];
+            const bool skip = (d == 0);
+            cplx out[3][8];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
+#pragma unroll 1
+            for (int r = 0; r < 3; r++, tile++) {
+                const int buf = tile % kBrRing;
+                const int use = tile / kBrRing;
+                if (producer && tile >= 1 && tile - 1 + kBrRing < kTiles) {
+                    const int pb = (tile - 1) % kBrRing, puse = (tile - 1) / kBrRing;
+                    mbar_wait(empty + pb, puse & 1);
+                    tma_load_tile(ring + pb * kBrTileBytes, bsk_bytes + (size_t)(tile - 1 + kBrRing) * kBrTileBytes, kBrTileBytes, full + pb);
+                }
+                __syncwarp();
+                if (!skip) {
+                    cplx v[8];
+                    const u64x2 *p = acc + r * 512;
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        const int jj = t + 64 * m;
+                        const int e0 = (jj - d) & 2047;
+                        const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];
+                        const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
+                        const bool sw = (e0 & 512) != 0;
+                        const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
+                        const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
+                        const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
+                        const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
+                        v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
+                                    digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
+                    }
+                    cplx *s = flip ? scr1 : scr0;
+                    flip ^= 1;
+                    if (TILES == 1) group_sync(bar_war);  // the partner warp has finished reading the single tile
+                    fwd_p1_tm(v, s, tm, t);
+                    group_sync(bar);
+                    fwd_p2x_tm(v, s, tm, t);
+                    exchange8<-1>(v, t & 7);
+                    const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
+                    mbar_wait(full + buf, use & 1);
+                    if (PRE) {
+                        cplx kc[8], kn[8];
+#pragma unroll
+                        for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];
+                        fwd_p3x(v);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            if (c < 2) {
+#pragma unroll
+                                for (int k3 = 0; k3 < 8; k3++) kn[k3] = key[(c + 1) * 512 + k3 * 64];
+                            }
+#pragma unroll
+                            for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], kc[k3]);
+#pragma unroll
+                            for (int k3 = 0; k3 < 8; k3++) kc[k3] = kn[k3];
+                        }
+                    } else {
+                        fwd_p3x(v);
+#pragma unroll
+                        for (int c = 0; c < 3; c++)
+#pragma unroll
+                            for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[c * 512 + k3 * 64]);
+                    }
+                } else {
+                    mbar_wait(full + buf, use & 1);
+                }
+                mbar_arrive(empty + buf);
+            }
+            if (skip) continue;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                cplx *s = flip ? scr1 : scr0;
+                flip ^= 1;
+                inv_p3x(out[c]);
+                exchange8<1>(out[c], t & 7);
+                if (TILES == 1) group_sync(bar_war);
+                inv_p2x_tm(out[c], s, tm, t);
+                group_sync(bar);
+                inv_p1_tm(out[c], s, tm, t);
+                u64x2 *p = acc + c * 512;
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    u64x2 w = p[t + 64 * m];
+                    w.lo += torus_from_scaled(out[c][m].x);
+                    w.hi += torus_from_scaled(out[c][m].y);
+                    p[t + 64 * m] = w;
+                }
+            }
+        }
+        group_sync(bar);
+        uint64_t *o = acc_out + (size_t)ct * kGlweWords;
+        for (int w = t; w < 3 * 512; w += 64) {
+            const u64x2 x = acc[w];
+            const int c = w >> 9, jj = w & 511;
+            o[c * 1024 + jj] = x.lo;
+            o[c * 1024 + jj + 512] = x.hi;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 256);
+}
+
 // Other decompositions measured on B200 and rejected (tools/brbench.py, 1024 ciphertexts):
 //   * one polynomial per 64-thread sub-group, three sub-groups per ciphertext, spectra exchanged through
 //     the transpose tiles (per-step latency 15.9 k -> 9.3 k cycles, but only 2 ciphertexts fit per SM):
@@ -882,6 +1162,27 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         const int teams = n <= sms ? 1 : kLlTeams;
         k_blind_rotate_ll<<<(n + teams - 1) / teams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(in, out, n, K.bsk_f, K.tw, teams);
     };
+    {  // experimental variants (development only)
+        static const int variant = [] {
+            const char *e = getenv("CBS_BR_VARIANT");
+            return e ? atoi(e) : 0;
+        }();
+        static std::once_flag once6[64];
+        if (variant >= 64) {
+            std::call_once(once6[dev], [&] {
+                cudaFuncSetAttribute(k_blind_rotate_v6<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br6<4, 2>::kSmemBytes);
+                cudaFuncSetAttribute(k_blind_rotate_v6<5, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br6<5, 1>::kSmemBytes);
+                cudaFuncSetAttribute(k_blind_rotate_v6<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br6<4, 1>::kSmemBytes);
+            });
+            if (variant == 64)
+                k_blind_rotate_v6<4, 2, true><<<(count + 3) / 4, 256, Br6<4, 2>::kSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+            else if (variant == 65)
+                k_blind_rotate_v6<5, 1, false><<<(count + 4) / 5, 320, Br6<5, 1>::kSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+            else
+                k_blind_rotate_v6<4, 1, false><<<(count + 3) / 4, 256, Br6<4, 1>::kSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
+            return;
+        }
+    }
     // small batches (at most kLlTeams ciphertexts per SM): the 192-thread-team kernel, 2.4x shorter per blind rotation
     if (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * sms)) {
         launch_team(lwe, acc, count);

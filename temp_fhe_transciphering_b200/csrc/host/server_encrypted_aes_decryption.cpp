@@ -58,7 +58,9 @@ int main(int argc, char **argv)
 
     std::vector<uint64_t> result((size_t)nblocks * 128 * CBS_LWE_BIG_WORDS);
     if (getenv("CBS_STAGE_TIMING")) {  // separate the driver / primary-context start-up from our own set-up
-        for (int g = 0; g < ngpu; g++) cbs_device_init(g);
+        std::vector<std::thread> init;  // in parallel, like the worker threads would do it implicitly
+        for (int g = 0; g < ngpu; g++) init.emplace_back([g]() { cbs_device_init(g); });
+        for (auto &th : init) th.join();
         clk.mark("cuda_init");
     }
     std::vector<double> t_ctx(ngpu, 0.0), t_run(ngpu, 0.0);

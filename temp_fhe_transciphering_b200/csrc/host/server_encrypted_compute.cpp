@@ -51,7 +51,9 @@ int main(int argc, char **argv)
     const size_t vw = (size_t)16 * CBS_LWE_BIG_WORDS;   // words per value
     std::vector<uint64_t> out(vw);
     if (getenv("CBS_STAGE_TIMING")) {
-        for (int g = 0; g < ngpu; g++) cbs_device_init(g);
+        std::vector<std::thread> init;
+        for (int g = 0; g < ngpu; g++) init.emplace_back([g]() { cbs_device_init(g); });
+        for (auto &th : init) th.join();
         clk.mark("cuda_init");
     }
 

@@ -63,21 +63,28 @@ inline bool read_hex_file(const std::string &path, std::vector<uint8_t> &out)
 // processes: on an 8 x B200 box cuInit + primary contexts cost 5.4 - 8.6 s with all eight GPUs visible against 0.8 - 3 s
 // with one (profiles/r02_harness_{1,8}gpu.jsonl), while a GPU transciphers ~62 blocks per second.  Minimising
 // t(g) = 0.85 g + blocks / (62 g) gives g = sqrt(blocks / 53): one GPU up to ~120 blocks, 4 - 5 for 1024.  The choice is made
-// effective by narrowing CUDA_VISIBLE_DEVICES (unless the caller set it, or CBS_GPUS asks for a specific count), so that
-// the driver never touches the other devices.  block_equivalents = AES blocks (stage 7) or values / 8 (stage 8).
+// effective by narrowing CUDA_VISIBLE_DEVICES (to the first g entries of the caller's list if there is one; CBS_GPUS asks
+// for a specific count), so that the driver never touches the other devices.  block_equivalents = AES blocks (stage 7) or values / 8 (stage 8).
 inline void plan_visible_gpus(long block_equivalents)
 {
-    if (getenv("CUDA_VISIBLE_DEVICES")) return;  // the caller's choice
-    int present = 0;
-    for (int i = 0; i < 64; i++) {
-        const std::string dev = "/dev/nvidia" + std::to_string(i);
-        if (FILE *f = fopen(dev.c_str(), "r")) {
-            fclose(f);
-            present++;
-        } else if (access(dev.c_str(), F_OK) == 0) {
-            present++;
+    // the devices this process may use: the caller's CUDA_VISIBLE_DEVICES list if there is one, else /dev/nvidia<i>
+    std::vector<std::string> avail;
+    if (const char *cvd = getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string tok;
+        for (const char *p = cvd;; p++) {
+            if (*p == ',' || *p == '\0') {
+                if (!tok.empty()) avail.push_back(tok);
+                tok.clear();
+                if (*p == '\0') break;
+            } else if (!isspace((unsigned char)*p)) {
+                tok.push_back(*p);
+            }
         }
+    } else {
+        for (int i = 0; i < 64; i++)
+            if (access(("/dev/nvidia" + std::to_string(i)).c_str(), F_OK) == 0) avail.push_back(std::to_string(avail.size()));
     }
+    const int present = (int)avail.size();
     if (present <= 1) return;
     int want = 1;
     if (const char *e = getenv("CBS_GPUS")) {
@@ -87,8 +94,10 @@ inline void plan_visible_gpus(long block_equivalents)
     }
     want = want < 1 ? 1 : (want > present ? present : want);
     std::string list;
-    for (int i = 0; i < want; i++) list += (i ? "," : "") + std::to_string(i);
+    for (int i = 0; i < want; i++) list += (i ? "," : "") + avail[(size_t)i];
     setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
+    if (getenv("CBS_PLAN_DEBUG")) fprintf(stderr, "[plan] %ld block equivalents, %d device(s) available -> CUDA_VISIBLE_DEVICES=%s\n",
+                                          block_equivalents, present, list.c_str());
 }
 
 // Wall-clock breakdown of a stage process (the harness only records the total per stage, harness/utils.py:85-109).

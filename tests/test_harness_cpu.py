@@ -45,3 +45,22 @@ def test_layout_is_what_run_submission_expects(tmp_path, size):
     ref = "/root/reference/harness/run_submission.py"
     if os.path.exists(ref):
         assert open(ref, "rb").read() == (tmp_path / "harness" / "run_submission.py").read_bytes()
+
+
+@pytest.mark.parametrize("nblocks,cvd,gpus,want", [(1, "3,5,6", None, "3"), (64, "0,1,2,3,4,5,6,7", None, "0"),
+                                                   (1024, "0,1,2,3,4,5,6,7", None, "0,1,2,3"), (8, "4,5", "2", "4,5"),
+                                                   (4000, "0,1,2,3,4,5,6,7", None, "0,1,2,3,4,5,6,7")])
+def test_stage_executable_plans_its_gpu_count_before_cuda_starts(tmp_path, nblocks, cvd, gpus, want):
+    """stage_common.h plan_visible_gpus: driver start-up dominates a one-shot stage process (0.8 s with one GPU visible,
+    5-9 s with eight), so stage 7 narrows CUDA_VISIBLE_DEVICES to sqrt(blocks / 53) devices before its first CUDA call."""
+    import subprocess
+    (tmp_path / "datasets" / "toy").mkdir(parents=True)
+    (tmp_path / "datasets" / "toy" / "db.hex").write_text("00" * 16 * nblocks)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=cvd, CBS_PLAN_DEBUG="1")
+    env.pop("CBS_GPUS", None)
+    if gpus:
+        env["CBS_GPUS"] = gpus
+    exe = os.path.join(harness_run.BIN, "server_encrypted_aes_decryption")
+    p = subprocess.run([exe, "0"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=60)
+    assert p.returncode != 0  # no keys in this directory: it stops right after the plan
+    assert f"CUDA_VISIBLE_DEVICES={want}\n" in p.stderr, p.stderr
