@@ -489,183 +489,16 @@ __device__ __forceinline__ void fill_t2_table(cplx *t2tab, const double *twtab, 
     }
 }
 
-constexpr int kBr3GroupSmem = kGlweWords * 8 + 2 * 512 * 16;                         // 40 KB
-constexpr int kBr3SmemBytes = kBrGroups * kBr3GroupSmem + kBrRing * kBrTileBytes + 64 + kBrGroups * kLweN * 2;  // + mbarriers + rotations
-
-// The pass-2 <-> pass-3 transposes of all six transforms go through width-8 warp shuffles (fft512.cuh,
-// shuffle-exchange variant) instead of shared memory: 432 fewer shared-memory wavefronts per step and
-// ciphertext (ncu r01: the shared-memory data pipe, not FP64, was the busiest unit) and 6 instead of 12 group
+// ---- v4: the production blind rotation = v3 (TMA ring, paired accumulator, shuffle-exchange transforms) with the per-thread
+// twiddles in TENSOR MEMORY.  v3 kept the 16 complex pass-1 / pass-2 twiddles of a thread in 64 of its 246 registers.
+// Blackwell's tensor memory (256 KB per SM, idle in an FP64 kernel) is addressable per lane with tcgen05.ld/st (SASS
+// LDTM/STTM): every thread parks its twiddles there once and fetches four at a time right before the multiply
+// (tools/bench_tmem.cu: 360-470 B/clk/SM, 22-35 cycles, no interference with the shared-memory pipe).  ptxas spends the
+// freed registers on deeper load/FMA scheduling: 5.53 instead of 5.80 ms per wave of 592 ciphertexts (-4.8 %), FP64 pipe
+// 62 % of a step.  (More groups per SM at the 168-register cap of a 320/384-thread CTA lose: profiles/r02_brbench_variants.txt.)
+// The pass-2 <-> pass-3 transposes of all six transforms go through width-8 warp shuffles (fft512.cuh, shuffle-exchange
+// variant) instead of shared memory: 432 fewer shared-memory wavefronts per step and ciphertext and 6 instead of 12 group
 // barriers per step.  The BSK stays in the plain transform's layout.
-// (Tried and rejected: a producer lane that polls the ring's `empty` barriers with mbarrier.test_wait at four points of
-//  every polynomial instead of blocking at the top of it: 6.04 vs 5.83 ms per wave.)
-__global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v3(const uint64_t *__restrict__ lwe,
-                                                                        uint64_t *__restrict__ acc_out, int count,
-                                                                        const double *__restrict__ bsk_f,
-                                                                        const double *__restrict__ twtab, int groups,
-                                                                        int ct_base)
-{
-    // `groups` (<= kBrGroups) ciphertexts per CTA, first ciphertext of the launch = ct_base; `count` is the
-    // exclusive upper bound.  The launcher uses groups < kBrGroups to balance the last wave.
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6;
-    const int ct = (gi < groups) ? ct_base + blockIdx.x * groups + gi : count;
-    unsigned char *ring = smem_raw + (size_t)kBrGroups * kBr3GroupSmem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBrRing * kBrTileBytes);
-    uint64_t *empty = full + kBrRing;
-    const int active_groups = min(groups, count - (ct_base + blockIdx.x * groups));
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < kBrRing; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, 64 * active_groups);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (ct >= count) return;
-    const bool producer = (threadIdx.x == 0);
-    const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
-    constexpr int kTiles = kLweN * 3;
-    if (producer)
-        for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
-    __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-
-    unsigned char *base = smem_raw + (size_t)gi * kBr3GroupSmem;
-    u64x2 *acc = reinterpret_cast<u64x2 *>(base);  // [3][512] pairs (coef j, coef j + 512)
-    const int t = threadIdx.x & 63;
-    const int bar = 1 + gi;
-    cplx *scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
-    cplx *scr1 = scr0 + 512;
-    int flip = 0;
-    const uint64_t *a = lwe + (size_t)ct * kLweSmall;
-    // all 768 mod-switched rotation amounts up front: no global-load latency inside the step loop
-    uint16_t *rot = reinterpret_cast<uint16_t *>(ring + kBrRing * kBrTileBytes + 64) + gi * kLweN;
-    for (int q = t; q < kLweN; q += 64) rot[q] = (uint16_t)(modswitch_dev(a[q]) & 2047);
-    {
-        const int bt = modswitch_dev(a[kLweN]);
-        for (int jj = t; jj < 512; jj += 64) {
-            acc[jj] = u64x2{0, 0};
-            acc[512 + jj] = u64x2{0, 0};
-            u64x2 b;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int j = jj + 512 * h;
-                const int e = (j + bt) & 2047;
-                const int i = e & 1023;
-                uint64_t val = 1ull << (61 - 2 * (i & 7));
-                const bool neg = (i < 512) != ((e & 1024) != 0);
-                (h ? b.hi : b.lo) = neg ? (0ull - val) : val;
-            }
-            acc[1024 + jj] = b;
-        }
-    }
-    group_sync(bar);
-
-    // Twiddles struct view for the shared phase functions that still take t1
-    Twiddles tw;
-    load_twiddles_x(tw, twtab, t);
-
-    int tile = 0;
-#pragma unroll 1
-    for (int i = 0; i < kLweN; i++) {
-        const int d = rot[i];
-        const bool skip = (d == 0);
-        cplx out[3][8];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
-#pragma unroll 1
-        for (int r = 0; r < 3; r++, tile++) {
-            const int buf = tile % kBrRing;
-            const int use = tile / kBrRing;
-            if (producer && tile >= 1 && tile - 1 + kBrRing < kTiles) {
-                const int pb = (tile - 1) % kBrRing, puse = (tile - 1) / kBrRing;
-                mbar_wait(empty + pb, puse & 1);
-                tma_load_tile(ring + pb * kBrTileBytes, bsk_bytes + (size_t)(tile - 1 + kBrRing) * kBrTileBytes, kBrTileBytes,
-                              full + pb);
-            }
-            __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-            if (!skip) {
-                cplx v[8];
-                const u64x2 *p = acc + r * 512;
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const int jj = t + 64 * m;
-                    const int e0 = (jj - d) & 2047;
-                    const uint4 src = reinterpret_cast<const uint4 *>(p)[e0 & 511];  // (lo.l, lo.h, hi.l, hi.h)
-                    const uint4 own = reinterpret_cast<const uint4 *>(p)[jj];
-                    // quarter h = e0 >> 9 of the 2N-periodic extension:
-                    //   (rot_lo, rot_hi) = h0:(lo,hi) h1:(hi,-lo) h2:(-lo,-hi) h3:(-hi,lo)
-                    // swap on bit 9, negate rot_lo on bit 10, rot_hi on bit 9 ^ bit 10.  ncu showed this integer glue at
-                    // 19 % of the kernel's issue slots (55 instructions per point with 64-bit selects, negations and
-                    // compares); only the high word of each difference is needed for the one-level digit.
-                    const bool sw = (e0 & 512) != 0;
-                    const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
-                    const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
-                    const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
-                    const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
-                    v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
-                                digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
-                }
-                cplx *s = flip ? scr1 : scr0;
-                flip ^= 1;
-                fwd_p1(v, s, tw, t);
-                group_sync(bar);
-                fwd_p2x(v, s, tw, t);
-                exchange8<-1>(v, t & 7);
-                const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
-                mbar_wait(full + buf, use & 1);  // requested a whole FFT ago: normally already complete
-                cplx kc[8], kn[8];
-#pragma unroll
-                for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];  // column 0, overlaps the last pass
-                fwd_p3x(v);
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    if (c < 2) {
-#pragma unroll
-                        for (int k3 = 0; k3 < 8; k3++) kn[k3] = key[(c + 1) * 512 + k3 * 64];
-                    }
-#pragma unroll
-                    for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], kc[k3]);
-#pragma unroll
-                    for (int k3 = 0; k3 < 8; k3++) kc[k3] = kn[k3];
-                }
-            } else {
-                mbar_wait(full + buf, use & 1);
-            }
-            mbar_arrive(empty + buf);
-        }
-        if (skip) continue;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            cplx *s = flip ? scr1 : scr0;
-            flip ^= 1;
-            inv_p3x(out[c]);
-            exchange8<1>(out[c], t & 7);
-            inv_p2x(out[c], s, tw, t);
-            group_sync(bar);
-            inv_p1(out[c], s, tw, t);
-            u64x2 *p = acc + c * 512;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                u64x2 w = p[t + 64 * m];
-                w.lo += torus_from_scaled(out[c][m].x);
-                w.hi += torus_from_scaled(out[c][m].y);
-                p[t + 64 * m] = w;
-            }
-        }
-    }
-    group_sync(bar);
-    uint64_t *o = acc_out + (size_t)ct * kGlweWords;
-    for (int w = t; w < 3 * 512; w += 64) {
-        const u64x2 x = acc[w];
-        const int c = w >> 9, jj = w & 511;
-        o[c * 1024 + jj] = x.lo;
-        o[c * 1024 + jj + 512] = x.hi;
-    }
-}
-
-// ---- v6 (experimental, CBS_BR_VARIANT=64/65): v3 with the per-thread twiddles in tensor memory --------------------------
 __device__ __forceinline__ void tmem_alloc_cols(uint32_t *slot, int cols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
@@ -757,25 +590,22 @@ __device__ __forceinline__ void inv_p1_tm(cplx v[8], const cplx *scr, uint32_t t
     for (int m = 1; m < 8; m++) v[m] = cmul_conj(v[m], cplx{cr[m], ci[m]});
 }
 
-template <int G, int TILES>
-struct Br6 {
-    static constexpr int kGroupSmem = kGlweWords * 8 + TILES * 8192;
-    static constexpr int kRingOff = G * kGroupSmem;
-    static constexpr int kBarOff = kRingOff + kBrRing * kBrTileBytes;
-    static constexpr int kRotOff = kBarOff + 64;
-    static constexpr int kSmemBytes = kRotOff + G * kLweN * 2;
-};
+constexpr int kBr4GroupSmem = kGlweWords * 8 + 2 * 8192;   // accumulator 24 KB + 2 transpose tiles
+constexpr int kBr4RingOff = kBrGroups * kBr4GroupSmem;
+constexpr int kBr4BarOff = kBr4RingOff + kBrRing * kBrTileBytes;
+constexpr int kBr4RotOff = kBr4BarOff + 64;                  // 2 x 2 mbarriers + tensor-memory slot
+constexpr int kBr4SmemBytes = kBr4RotOff + kBrGroups * kLweN * 2;
 
-template <int G, int TILES, bool PRE>
-__global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v6(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out, int count,
-                                                                const double *__restrict__ bsk_f, const double *__restrict__ twtab)
+__global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v4(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out,
+                                                                        int count, const double *__restrict__ bsk_f,
+                                                                        const double *__restrict__ twtab)
 {
-    using L = Br6<G, TILES>;
+    constexpr int G = kBrGroups;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int gi = threadIdx.x >> 6, warp = threadIdx.x >> 5;
     const int ct = blockIdx.x * G + gi;
-    unsigned char *ring = smem_raw + L::kRingOff;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L::kBarOff);
+    unsigned char *ring = smem_raw + kBr4RingOff;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kBr4BarOff);
     uint64_t *empty = full + kBrRing;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + kBrRing);
     const int active_groups = min(G, count - blockIdx.x * G);
@@ -808,14 +638,15 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v6(const uint64_t *_
         if (producer)
             for (int b = 0; b < kBrRing; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
         __syncwarp();
-        unsigned char *base = smem_raw + (size_t)gi * L::kGroupSmem;
-        u64x2 *acc = reinterpret_cast<u64x2 *>(base);
-        const int bar = 1 + gi, bar_war = 1 + G + gi;
+        unsigned char *base = smem_raw + (size_t)gi * kBr4GroupSmem;
+        u64x2 *acc = reinterpret_cast<u64x2 *>(base);  // [3][512] pairs (coef j, coef j + 512)
+        const int bar = 1 + gi;
         cplx *scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
-        cplx *scr1 = scr0 + (TILES == 2 ? 512 : 0);
+        cplx *scr1 = scr0 + 512;  // two tiles used alternately: no write-after-read barrier between transforms
         int flip = 0;
         const uint64_t *a = lwe + (size_t)ct * kLweSmall;
-        uint16_t *rot = reinterpret_cast<uint16_t *>(smem_raw + L::kRotOff) + gi * kLweN;
+        // all 768 mod-switched rotation amounts up front: no global-load latency inside the step loop
+        uint16_t *rot = reinterpret_cast<uint16_t *>(smem_raw + kBr4RotOff) + gi * kLweN;
         for (int q = t; q < kLweN; q += 64) rot[q] = (uint16_t)(modswitch_dev(a[q]) & 2047);
         {
             const int bt = modswitch_dev(a[kLweN]);
@@ -875,35 +706,26 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v6(const uint64_t *_
                     }
                     cplx *s = flip ? scr1 : scr0;
                     flip ^= 1;
-                    if (TILES == 1) group_sync(bar_war);  // the partner warp has finished reading the single tile
                     fwd_p1_tm(v, s, tm, t);
                     group_sync(bar);
                     fwd_p2x_tm(v, s, tm, t);
                     exchange8<-1>(v, t & 7);
                     const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
                     mbar_wait(full + buf, use & 1);
-                    if (PRE) {
-                        cplx kc[8], kn[8];
+                    cplx kc[8], kn[8];  // tile reads software-pipelined against the multiply-accumulate
 #pragma unroll
-                        for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];
-                        fwd_p3x(v);
+                    for (int k3 = 0; k3 < 8; k3++) kc[k3] = key[k3 * 64];  // column 0, overlaps the last pass
+                    fwd_p3x(v);
 #pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            if (c < 2) {
+                    for (int c = 0; c < 3; c++) {
+                        if (c < 2) {
 #pragma unroll
-                                for (int k3 = 0; k3 < 8; k3++) kn[k3] = key[(c + 1) * 512 + k3 * 64];
-                            }
-#pragma unroll
-                            for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], kc[k3]);
-#pragma unroll
-                            for (int k3 = 0; k3 < 8; k3++) kc[k3] = kn[k3];
+                            for (int k3 = 0; k3 < 8; k3++) kn[k3] = key[(c + 1) * 512 + k3 * 64];
                         }
-                    } else {
-                        fwd_p3x(v);
 #pragma unroll
-                        for (int c = 0; c < 3; c++)
+                        for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], kc[k3]);
 #pragma unroll
-                            for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[c * 512 + k3 * 64]);
+                        for (int k3 = 0; k3 < 8; k3++) kc[k3] = kn[k3];
                     }
                 } else {
                     mbar_wait(full + buf, use & 1);
@@ -917,7 +739,6 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v6(const uint64_t *_
                 flip ^= 1;
                 inv_p3x(out[c]);
                 exchange8<1>(out[c], t & 7);
-                if (TILES == 1) group_sync(bar_war);
                 inv_p2x_tm(out[c], s, tm, t);
                 group_sync(bar);
                 inv_p1_tm(out[c], s, tm, t);
@@ -956,7 +777,7 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v6(const uint64_t *_
 //     occupancy): 13.7 ms, 136 B of spills;
 //   * pass-2 twiddles in a shared table: 13.3 ms; balancing the last wave with 3-group CTAs: -2 % only,
 //     because a group's step is a latency chain that does not speed up when its neighbours leave.
-// Per-step cycle budget of a v3 group (clock64 probes, round 1): build 4.2 k, forward passes 3.3 k, pass 3 + MAC 2.8 k,
+// Per-step cycle budget of a group before the twiddles moved to tensor memory (clock64 probes, round 1): build 4.2 k, forward passes 3.3 k, pass 3 + MAC 2.8 k,
 // inverse 4.2 k, torus + update 1.5 k, tile wait 0.5 k.
 // Round 2, all parity-green on B200 and all slower (code in git history, commit 1d4... "Blind rotation experiments";
 // numbers in profiles/r02_brbench_variants.txt, ncu summaries profiles/r02_br_*_ncu.txt):
@@ -973,7 +794,7 @@ __global__ void __launch_bounds__(64 * G, 1) k_blind_rotate_v6(const uint64_t *_
 //     tensor memory): 130 KB of code (stall_no_instruction 0.77 per issue) and a 4-tile ring: 18.1 ms per 1184.
 
 // ---- low-latency blind rotation for small batches -------------------------------------------------------------
-// k_blind_rotate_v3 keeps one ciphertext per 64-thread group, so a step is a serial chain of 3 builds, 6 transforms and
+// k_blind_rotate_v4 keeps one ciphertext per 64-thread group, so a step is a serial chain of 3 builds, 6 transforms and
 // 9 products (~15.9 k cycles, 5.8 ms per blind rotation) however few ciphertexts there are.  The toy instance (128
 // ciphertexts per round), the upper levels of the max tree and most layers of the inner-product circuit are far below
 // one wave (592), so for <= 2 ciphertexts per SM a TEAM of 192 threads owns one ciphertext: sub-group r builds and
@@ -1147,7 +968,7 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     dev &= 63;
     std::call_once(once[dev], [&] {
         cudaFuncSetAttribute(k_blind_rotate_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, kLlSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr3SmemBytes);
+        cudaFuncSetAttribute(k_blind_rotate_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr4SmemBytes);
         int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         sm_count[dev] = n > 0 ? n : 1;
@@ -1162,27 +983,6 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         const int teams = n <= sms ? 1 : kLlTeams;
         k_blind_rotate_ll<<<(n + teams - 1) / teams, kLlTeamThreads * kLlTeams, kLlSmemBytes, s>>>(in, out, n, K.bsk_f, K.tw, teams);
     };
-    {  // experimental variants (development only)
-        static const int variant = [] {
-            const char *e = getenv("CBS_BR_VARIANT");
-            return e ? atoi(e) : 0;
-        }();
-        static std::once_flag once6[64];
-        if (variant >= 64) {
-            std::call_once(once6[dev], [&] {
-                cudaFuncSetAttribute(k_blind_rotate_v6<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br6<4, 2>::kSmemBytes);
-                cudaFuncSetAttribute(k_blind_rotate_v6<5, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br6<5, 1>::kSmemBytes);
-                cudaFuncSetAttribute(k_blind_rotate_v6<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br6<4, 1>::kSmemBytes);
-            });
-            if (variant == 64)
-                k_blind_rotate_v6<4, 2, true><<<(count + 3) / 4, 256, Br6<4, 2>::kSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-            else if (variant == 65)
-                k_blind_rotate_v6<5, 1, false><<<(count + 4) / 5, 320, Br6<5, 1>::kSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-            else
-                k_blind_rotate_v6<4, 1, false><<<(count + 3) / 4, 256, Br6<4, 1>::kSmemBytes, s>>>(lwe, acc, count, K.bsk_f, K.tw);
-            return;
-        }
-    }
     // small batches (at most kLlTeams ciphertexts per SM): the 192-thread-team kernel, 2.4x shorter per blind rotation
     if (ll_mode == 2 || (ll_mode == 1 && count <= kLlTeams * sms)) {
         launch_team(lwe, acc, count);
@@ -1192,7 +992,7 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     const int wave = sms * kBrGroups, rem = count % wave;
     int head = count;
     if (ll_mode == 1 && count > wave && rem > 0 && rem <= kLlTeams * sms) head = count - rem;
-    k_blind_rotate_v3<<<(head + kBrGroups - 1) / kBrGroups, 64 * kBrGroups, kBr3SmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw, kBrGroups, 0);
+    k_blind_rotate_v4<<<(head + kBrGroups - 1) / kBrGroups, 64 * kBrGroups, kBr4SmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw);
     if (head < count) launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, count - head);
 }
 
@@ -1280,11 +1080,11 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     const int t = threadIdx.x & 63;
     const int idx = blockIdx.x * kTr2Glwe + gl;
     unsigned char *ring = smem_raw + (size_t)kTr2Glwe * kTr3UnitSmem;  // lane (i, limb) at (limb*2 + i) * 24,576
-    cplx *t2tab = reinterpret_cast<cplx *>(ring + 4 * kBrTileBytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + 4 * kBrTileBytes + 1024);
     uint64_t *empty = full + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + 4);
+    const int warp = threadIdx.x >> 5;
     const int active_units = min(kTr2Glwe, count - blockIdx.x * kTr2Glwe);
-    fill_t2x_table(t2tab, twtab, threadIdx.x);
     if (threadIdx.x == 0) {
         for (int b = 0; b < 4; b++) {
             mbar_init(full + b, 1);
@@ -1292,196 +1092,212 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 0) tmem_alloc_cols(tmem_slot, 128);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (idx >= count) return;
-    const bool producer = (threadIdx.x == 0);
-    const char *key_bytes = reinterpret_cast<const char *>(auto_f);
-    // tile of use n = s*3 + tt (level lev = 2 - tt), lane (i, sp): Fourier polys [s][i][sp][lev][0..2]
-    auto tile_src = [&](int n, int i, int sp) {
-        const int s = n / 3, lev = 2 - (n % 3);
-        return key_bytes + (size_t)((((s * 2 + i) * 2 + sp) * 3 + lev) * 3) * kFourierPolyDoubles * 8;
-    };
-    // refill of the four ring lanes for use n: `early` only takes the lanes every consumer has already released
-    // (non-blocking test right after a level's products), the regular call one barrier into the next transform
-    // blocks for the rest.  issued = bit mask of the lanes already requested for the pending use.
-    int issued = 0;
-    auto produce = [&](int n, bool early) {
-        if (n >= 30) return;
-#pragma unroll
-        for (int L = 0; L < 4; L++) {
-            if (issued & (1 << L)) continue;
-            if (n > 0) {
-                if (early) {
-                    if (!mbar_test(empty + L, (n - 1) & 1)) continue;
-                } else {
-                    mbar_wait(empty + L, (n - 1) & 1);
-                }
-            }
-            tma_load_tile(ring + L * kBrTileBytes, tile_src(n, L & 1, L >> 1), kBrTileBytes, full + L);
-            issued |= 1 << L;
-        }
-        if (!early) issued = 0;
-    };
-    if (producer) produce(0, false);
-    __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-    int want = -1;  // next ring refill the producer owes (issued one barrier into the following transform)
-
-    const cplx *t2s = t2tab + (t & 7);
-    unsigned char *base = smem_raw + (size_t)gl * kTr3UnitSmem;
-    u64x2 *cur = reinterpret_cast<u64x2 *>(base);
-    cplx *scr = reinterpret_cast<cplx *>(base + kGlweWords * 8 + sub * 8192);
-    cplx *X = reinterpret_cast<cplx *>(base + kGlweWords * 8 + 16384);  // [sub 2][512]
-    const int sbar = 1 + gl * 2 + sub;
-    const int ubar = 5 + gl;
-    Twiddles tw;
-    load_twiddles_x(tw, twtab, t);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // the 16 complex twiddles of a thread live in tensor memory (see k_blind_rotate_v4): 64 columns per warp, the two warps
+    // of a lane quarter side by side
+    const uint32_t tm = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
     {
-        const int u = threadIdx.x & 127;
-        if (from_acc) {
-            const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
-            const int lvl = idx % kCbsLevel;
-            for (int w = u; w < 3 * 512; w += 128) {
-                const int p = w >> 9, jj = w & 511;
-                cur[w] = u64x2{glev_pre_word(acc, lvl, p, jj), glev_pre_word(acc, lvl, p, jj + 512)};
-            }
-        } else {
-            const uint64_t *src = in + (size_t)idx * kGlweWords;
-            for (int w = u; w < 3 * 512; w += 128) {
-                const int p = w >> 9, jj = w & 511;
-                cur[w] = u64x2{src[p * 1024 + jj], src[p * 1024 + jj + 512]};
-            }
-        }
+        Twiddles tw;
+        load_twiddles_x(tw, twtab, t);
+        tmem_st_c4(tm, tw.t1);
+        tmem_st_c4(tm + 16, tw.t1 + 4);
+        tmem_st_c4(tm + 32, tw.t2);
+        tmem_st_c4(tm + 48, tw.t2 + 4);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    unit_sync(ubar);
+    if (idx < count) {
+        const bool producer = (threadIdx.x == 0);
+        const char *key_bytes = reinterpret_cast<const char *>(auto_f);
+        // tile of use n = s*3 + tt (level lev = 2 - tt), lane (i, sp): Fourier polys [s][i][sp][lev][0..2]
+        auto tile_src = [&](int n, int i, int sp) {
+            const int s = n / 3, lev = 2 - (n % 3);
+            return key_bytes + (size_t)((((s * 2 + i) * 2 + sp) * 3 + lev) * 3) * kFourierPolyDoubles * 8;
+        };
+        // refill of the four ring lanes for use n: `early` only takes the lanes every consumer has already released
+        // (non-blocking test right after a level's products), the regular call one barrier into the next transform
+        // blocks for the rest.  issued = bit mask of the lanes already requested for the pending use.
+        int issued = 0;
+        auto produce = [&](int n, bool early) {
+            if (n >= 30) return;
+    #pragma unroll
+            for (int L = 0; L < 4; L++) {
+                if (issued & (1 << L)) continue;
+                if (n > 0) {
+                    if (early) {
+                        if (!mbar_test(empty + L, (n - 1) & 1)) continue;
+                    } else {
+                        mbar_wait(empty + L, (n - 1) & 1);
+                    }
+                }
+                tma_load_tile(ring + L * kBrTileBytes, tile_src(n, L & 1, L >> 1), kBrTileBytes, full + L);
+                issued |= 1 << L;
+            }
+            if (!early) issued = 0;
+        };
+        if (producer) produce(0, false);
+        __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
+        int want = -1;  // next ring refill the producer owes (issued one barrier into the following transform)
 
-#pragma unroll 1
-    for (int s = 0; s < 10; s++) {
-        const int kinv = c_kappa_inv[s];
-        uint64_t pk[16];
+        unsigned char *base = smem_raw + (size_t)gl * kTr3UnitSmem;
+        u64x2 *cur = reinterpret_cast<u64x2 *>(base);
+        cplx *scr = reinterpret_cast<cplx *>(base + kGlweWords * 8 + sub * 8192);
+        cplx *X = reinterpret_cast<cplx *>(base + kGlweWords * 8 + 16384);  // [sub 2][512]
+        const int sbar = 1 + gl * 2 + sub;
+        const int ubar = 5 + gl;
         {
-            const u64x2 *p = cur + sub * 512;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int jj = t + 64 * m;
-                const int e = (jj * kinv) & 2047;
-                const u64x2 A = p[e & 511];
-                const int h = e >> 9;
-                pk[2 * m] = pack_digits<13, 3, uint64_t>(pair_pick(A, h));
-                pk[2 * m + 1] = pack_digits<13, 3, uint64_t>(pair_pick(A, (h + kinv) & 3));
+            const int u = threadIdx.x & 127;
+            if (from_acc) {
+                const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
+                const int lvl = idx % kCbsLevel;
+                for (int w = u; w < 3 * 512; w += 128) {
+                    const int p = w >> 9, jj = w & 511;
+                    cur[w] = u64x2{glev_pre_word(acc, lvl, p, jj), glev_pre_word(acc, lvl, p, jj + 512)};
+                }
+            } else {
+                const uint64_t *src = in + (size_t)idx * kGlweWords;
+                for (int w = u; w < 3 * 512; w += 128) {
+                    const int p = w >> 9, jj = w & 511;
+                    cur[w] = u64x2{src[p * 1024 + jj], src[p * 1024 + jj + 512]};
+                }
             }
         }
-        u64x2 nb[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int jj = t + 64 * (4 * sub + q);
-            const int e = (jj * kinv) & 2047;
-            const u64x2 A = cur[1024 + (e & 511)];
-            const int h = e >> 9;
-            const u64x2 own = cur[1024 + jj];
-            nb[q] = u64x2{own.lo + pair_pick(A, h), own.hi + pair_pick(A, (h + kinv) & 3)};
-        }
         unit_sync(ubar);
-#pragma unroll
-        for (int q = 0; q < 4; q++) cur[1024 + t + 64 * (4 * sub + q)] = nb[q];
 
-        cplx acc[3][8];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
-#pragma unroll 1
-        for (int tt = 0; tt < 3; tt++) {
-            const int n = s * 3 + tt;
-            cplx v[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++)
-                v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m], tt)),
-                            i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m + 1], tt))};
-            fwd_p1(v, scr, tw, t);
-            group_sync(sbar);
-            if (producer && want >= 0) {
-                produce(want, false);
-                want = -1;
-            }
-            __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-            fwd_p2x_s(v, scr, t2s, t);
-            exchange8<-1>(v, t & 7);
-            fwd_p3x(v);
-            cplx *Xw = X + sub * 512 + t;
-            const cplx *Xr = X + (1 - sub) * 512 + t;
-#pragma unroll
-            for (int k3 = 0; k3 < 8; k3++) Xw[k3 * 64] = v[k3];
-            unit_sync(ubar);
-            // own spectrum x key(i = sub, limb = sub), partner spectrum x key(i = 1 - sub, limb = sub)
-            const int Lown = sub * 2 + sub, Loth = sub * 2 + (1 - sub);
-            mbar_wait(full + Lown, n & 1);
+    #pragma unroll 1
+        for (int s = 0; s < 10; s++) {
+            const int kinv = c_kappa_inv[s];
+            uint64_t pk[16];
             {
-                const cplx *key = reinterpret_cast<const cplx *>(ring + Lown * kBrTileBytes) + t;
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-#pragma unroll
-                    for (int k3 = 0; k3 < 8; k3++) cfma(acc[c][k3], v[k3], key[c * 512 + k3 * 64]);
-            }
-            mbar_arrive(empty + Lown);
-            mbar_wait(full + Loth, n & 1);
-            {
-                const cplx *key = reinterpret_cast<const cplx *>(ring + Loth * kBrTileBytes) + t;
-#pragma unroll
-                for (int k3 = 0; k3 < 8; k3++) {
-                    const cplx o = Xr[k3 * 64];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) cfma(acc[c][k3], o, key[c * 512 + k3 * 64]);
-                }
-            }
-            mbar_arrive(empty + Loth);
-            want = n + 1;
-            unit_sync(ubar);  // partner finished reading the exchange tile before it is rewritten
-            if (producer) produce(want, true);  // lanes both units have released are refilled right away
-            __syncwarp();
-        }
-        const int shift = sub ? 41 : 0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            inv_p3x(acc[c]);
-            exchange8<1>(acc[c], t & 7);
-            if (producer && want >= 0) {
-                produce(want, false);
-                want = -1;
-            }
-            __syncwarp();
-            inv_p2x_s(acc[c], scr, t2s, t);
-            group_sync(sbar);
-            inv_p1(acc[c], scr, tw, t);
-            u64x2 *p = cur + c * 512;
-            if (sub == 0) {
-#pragma unroll
+                const u64x2 *p = cur + sub * 512;
+    #pragma unroll
                 for (int m = 0; m < 8; m++) {
-                    u64x2 w = p[t + 64 * m];
-                    w.lo += torus_from_scaled(acc[c][m].x);
-                    w.hi += torus_from_scaled(acc[c][m].y);
-                    p[t + 64 * m] = w;
+                    const int jj = t + 64 * m;
+                    const int e = (jj * kinv) & 2047;
+                    const u64x2 A = p[e & 511];
+                    const int h = e >> 9;
+                    pk[2 * m] = pack_digits<13, 3, uint64_t>(pair_pick(A, h));
+                    pk[2 * m + 1] = pack_digits<13, 3, uint64_t>(pair_pick(A, (h + kinv) & 3));
                 }
+            }
+            u64x2 nb[4];
+    #pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int jj = t + 64 * (4 * sub + q);
+                const int e = (jj * kinv) & 2047;
+                const u64x2 A = cur[1024 + (e & 511)];
+                const int h = e >> 9;
+                const u64x2 own = cur[1024 + jj];
+                nb[q] = u64x2{own.lo + pair_pick(A, h), own.hi + pair_pick(A, (h + kinv) & 3)};
             }
             unit_sync(ubar);
-            if (sub == 1) {
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    u64x2 w = p[t + 64 * m];
-                    w.lo += torus_from_scaled(acc[c][m].x) << shift;
-                    w.hi += torus_from_scaled(acc[c][m].y) << shift;
-                    p[t + 64 * m] = w;
+    #pragma unroll
+            for (int q = 0; q < 4; q++) cur[1024 + t + 64 * (4 * sub + q)] = nb[q];
+
+            cplx acc[3][8];
+    #pragma unroll
+            for (int c = 0; c < 3; c++)
+    #pragma unroll
+                for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
+    #pragma unroll 1
+            for (int tt = 0; tt < 3; tt++) {
+                const int n = s * 3 + tt;
+                cplx v[8];
+    #pragma unroll
+                for (int m = 0; m < 8; m++)
+                    v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m], tt)),
+                                i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m + 1], tt))};
+                fwd_p1_tm(v, scr, tm, t);
+                group_sync(sbar);
+                if (producer && want >= 0) {
+                    produce(want, false);
+                    want = -1;
+                }
+                __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
+                fwd_p2x_tm(v, scr, tm, t);
+                exchange8<-1>(v, t & 7);
+                fwd_p3x(v);
+                cplx *Xw = X + sub * 512 + t;
+                const cplx *Xr = X + (1 - sub) * 512 + t;
+    #pragma unroll
+                for (int k3 = 0; k3 < 8; k3++) Xw[k3 * 64] = v[k3];
+                unit_sync(ubar);
+                // own spectrum x key(i = sub, limb = sub), partner spectrum x key(i = 1 - sub, limb = sub)
+                const int Lown = sub * 2 + sub, Loth = sub * 2 + (1 - sub);
+                mbar_wait(full + Lown, n & 1);
+                {
+                    const cplx *key = reinterpret_cast<const cplx *>(ring + Lown * kBrTileBytes) + t;
+    #pragma unroll
+                    for (int c = 0; c < 3; c++)
+    #pragma unroll
+                        for (int k3 = 0; k3 < 8; k3++) cfma(acc[c][k3], v[k3], key[c * 512 + k3 * 64]);
+                }
+                mbar_arrive(empty + Lown);
+                mbar_wait(full + Loth, n & 1);
+                {
+                    const cplx *key = reinterpret_cast<const cplx *>(ring + Loth * kBrTileBytes) + t;
+    #pragma unroll
+                    for (int k3 = 0; k3 < 8; k3++) {
+                        const cplx o = Xr[k3 * 64];
+    #pragma unroll
+                        for (int c = 0; c < 3; c++) cfma(acc[c][k3], o, key[c * 512 + k3 * 64]);
+                    }
+                }
+                mbar_arrive(empty + Loth);
+                want = n + 1;
+                unit_sync(ubar);  // partner finished reading the exchange tile before it is rewritten
+                if (producer) produce(want, true);  // lanes both units have released are refilled right away
+                __syncwarp();
+            }
+            const int shift = sub ? 41 : 0;
+    #pragma unroll
+            for (int c = 0; c < 3; c++) {
+                inv_p3x(acc[c]);
+                exchange8<1>(acc[c], t & 7);
+                if (producer && want >= 0) {
+                    produce(want, false);
+                    want = -1;
+                }
+                __syncwarp();
+                inv_p2x_tm(acc[c], scr, tm, t);
+                group_sync(sbar);
+                inv_p1_tm(acc[c], scr, tm, t);
+                u64x2 *p = cur + c * 512;
+                if (sub == 0) {
+    #pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        u64x2 w = p[t + 64 * m];
+                        w.lo += torus_from_scaled(acc[c][m].x);
+                        w.hi += torus_from_scaled(acc[c][m].y);
+                        p[t + 64 * m] = w;
+                    }
+                }
+                unit_sync(ubar);
+                if (sub == 1) {
+    #pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        u64x2 w = p[t + 64 * m];
+                        w.lo += torus_from_scaled(acc[c][m].x) << shift;
+                        w.hi += torus_from_scaled(acc[c][m].y) << shift;
+                        p[t + 64 * m] = w;
+                    }
                 }
             }
+            unit_sync(ubar);
         }
-        unit_sync(ubar);
+        uint64_t *dst = out + (size_t)idx * kGlweWords;
+        for (int w = threadIdx.x & 127; w < 3 * 512; w += 128) {
+            const u64x2 x = cur[w];
+            const int c = w >> 9, jj = w & 511;
+            dst[c * 1024 + jj] = x.lo;
+            dst[c * 1024 + jj + 512] = x.hi;
+        }
     }
-    uint64_t *dst = out + (size_t)idx * kGlweWords;
-    for (int w = threadIdx.x & 127; w < 3 * 512; w += 128) {
-        const u64x2 x = cur[w];
-        const int c = w >> 9, jj = w & 511;
-        dst[c * 1024 + jj] = x.lo;
-        dst[c * 1024 + jj + 512] = x.hi;
-    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 128);
 }
 
 // Round 2, measured and rejected (code in git history, "trace v4"): one 64-thread group per GLWE with the six keyswitch
