@@ -34,7 +34,7 @@ CBS_PER_BLOCK = 1152           # 9 bootstrapped rounds x 128 state bits (SURVEY.
 BR_MFLOP = 148.6               # FP64 MFLOP per blind rotation
 BSK_BYTES = 56_623_104         # Fourier bootstrapping key streamed once per launch
 BR_IO_BYTES = 30_728           # LWE in + accumulator out per blind rotation
-NCU_BR_CSV = "r02_blind_rotate_ncu_full.csv"   # ncu --set full of k_blind_rotate_v3 on the 512-ciphertext lane shape the step launches
+NCU_BR_CSV = "r02_blind_rotate_ncu_full.csv"   # ncu --set full of k_blind_rotate_v4 on the 512-ciphertext lane shape the step launches
 METRIC = "AES-128 blocks transciphered/sec"
 UNIT = "blocks/s"
 
@@ -445,7 +445,7 @@ def main_ours(args):
         achieved = BR_MFLOP * 1e6 * B / (br_ms * 1e-3) * 1e-12
         br_bytes = BSK_BYTES + B * BR_IO_BYTES
         roof = {
-            "kernel": "k_blind_rotate_v3", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "kernel": "k_blind_rotate_v4", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved / fp64_peak, "traffic": read_ncu_traffic(),
             "traffic_source": f"profiles/{NCU_BR_CSV} (ncu --set full, same kernel, same 512-ciphertext launch shape)",
             "peak_source": "FP64 FMA probe kernel, same run",
