@@ -766,234 +766,6 @@ __global__ void __launch_bounds__(64 * kBrGroups, 1) k_blind_rotate_v4(const uin
     if (warp == 0) tmem_dealloc_cols(*tmem_slot, 256);
 }
 
-__device__ __forceinline__ void tmem_ld_u4x8(uint32_t taddr, uint4 w[8])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(w[0].x), "=r"(w[0].y), "=r"(w[0].z), "=r"(w[0].w), "=r"(w[1].x), "=r"(w[1].y), "=r"(w[1].z), "=r"(w[1].w),
-          "=r"(w[2].x), "=r"(w[2].y), "=r"(w[2].z), "=r"(w[2].w), "=r"(w[3].x), "=r"(w[3].y), "=r"(w[3].z), "=r"(w[3].w),
-          "=r"(w[4].x), "=r"(w[4].y), "=r"(w[4].z), "=r"(w[4].w), "=r"(w[5].x), "=r"(w[5].y), "=r"(w[5].z), "=r"(w[5].w),
-          "=r"(w[6].x), "=r"(w[6].y), "=r"(w[6].z), "=r"(w[6].w), "=r"(w[7].x), "=r"(w[7].y), "=r"(w[7].z), "=r"(w[7].w)
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_u4x8(uint32_t taddr, const uint4 w[8])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-        "%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-        "r"(w[0].x), "r"(w[0].y), "r"(w[0].z), "r"(w[0].w), "r"(w[1].x), "r"(w[1].y), "r"(w[1].z), "r"(w[1].w), "r"(w[2].x),
-        "r"(w[2].y), "r"(w[2].z), "r"(w[2].w), "r"(w[3].x), "r"(w[3].y), "r"(w[3].z), "r"(w[3].w), "r"(w[4].x), "r"(w[4].y),
-        "r"(w[4].z), "r"(w[4].w), "r"(w[5].x), "r"(w[5].y), "r"(w[5].z), "r"(w[5].w), "r"(w[6].x), "r"(w[6].y), "r"(w[6].z),
-        "r"(w[6].w), "r"(w[7].x), "r"(w[7].y), "r"(w[7].z), "r"(w[7].w)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// ---- v7: the accumulator lives in TENSOR MEMORY, six ciphertexts per SM --------------------------------------------
-// What caps v4 at four groups per SM is shared memory: 24 KB of accumulator + 16 KB of transpose tiles per ciphertext and a
-// 48 KB key ring.  The accumulator only needs shared memory for the ROTATED read of the build (coefficient j - d belongs
-// to another thread); the owner's read-modify-write does not.  Here every thread keeps its own 24 accumulator pairs
-// (coefficients t + 64 m of the three polynomials) in 96 tensor-memory columns; the update is LDTM -> add -> STTM, and the
-// build stages the polynomial through a transient 8 KB tile (STS own -> group barrier -> LDS rotated), alternating with
-// the transpose tile, so a group needs 16 KB of shared memory instead of 40: SIX groups (12 warps, three per scheduler,
-// 168 registers) and a THREE-row key ring fit in 178 KB.  The twiddles of a lane quarter are shared by its three warps
-// (warps w, w + 4, w + 8 own the same thread half t), so tensor memory holds 64 + 3 x 96 columns per quarter.
-template <int G>
-struct Br7 {
-    static constexpr int kRing = 3;
-    static constexpr int kGroupSmem = 2 * 8192;  // two tiles used alternately (staging / transpose)
-    static constexpr int kRingOff = G * kGroupSmem;
-    static constexpr int kBarOff = kRingOff + kRing * kBrTileBytes;
-    static constexpr int kRotOff = kBarOff + 64;
-    static constexpr int kSmemBytes = kRotOff + G * kLweN * 2;
-};
-template <int G, int MAXT = 64 * G>
-__global__ void __launch_bounds__(MAXT, 1) k_blind_rotate_v7(const uint64_t *__restrict__ lwe, uint64_t *__restrict__ acc_out,
-                                                                int count, const double *__restrict__ bsk_f,
-                                                                const double *__restrict__ twtab)
-{
-    using L = Br7<G>;
-    constexpr int R = L::kRing;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gi = threadIdx.x >> 6, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ct = blockIdx.x * G + gi;
-    unsigned char *ring = smem_raw + L::kRingOff;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L::kBarOff);
-    uint64_t *empty = full + R;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + R);
-    const int active_groups = min(G, count - blockIdx.x * G);
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < R; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, 2 * active_groups);  // one arrive per warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tmem_alloc_cols(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tm = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16);  // twiddles of this lane quarter: columns [0, 64)
-    const uint32_t tm_own = tm + 64 + (uint32_t)(96 * (warp >> 2));
-    const int t = threadIdx.x & 63;
-    if (warp < 4) {
-        Twiddles tw;
-        load_twiddles_x(tw, twtab, t);
-        tmem_st_c4(tm, tw.t1);
-        tmem_st_c4(tm + 16, tw.t1 + 4);
-        tmem_st_c4(tm + 32, tw.t2);
-        tmem_st_c4(tm + 48, tw.t2 + 4);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (ct < count) {
-        const bool producer = (threadIdx.x == 0);
-        const char *bsk_bytes = reinterpret_cast<const char *>(bsk_f);
-        constexpr int kTiles = kLweN * 3;
-        if (producer)
-            for (int b = 0; b < R; b++) tma_load_tile(ring + b * kBrTileBytes, bsk_bytes + (size_t)b * kBrTileBytes, kBrTileBytes, full + b);
-        __syncwarp();
-        cplx *scr0 = reinterpret_cast<cplx *>(smem_raw + (size_t)gi * L::kGroupSmem);
-        cplx *scr1 = scr0 + 512;
-        const int bar = 1 + gi;
-        int flip = 0;
-        const uint64_t *a = lwe + (size_t)ct * kLweSmall;
-        uint16_t *rot = reinterpret_cast<uint16_t *>(smem_raw + L::kRotOff) + gi * kLweN;
-        for (int q = t; q < kLweN; q += 64) rot[q] = (uint16_t)(modswitch_dev(a[q]) & 2047);
-        {
-            const int bt = modswitch_dev(a[kLweN]);
-            uint4 z[8], own2[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int jj = t + 64 * m;
-                uint64_t b[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int j = jj + 512 * h;
-                    const int e = (j + bt) & 2047;
-                    const int i = e & 1023;
-                    uint64_t val = 1ull << (61 - 2 * (i & 7));
-                    const bool neg = (i < 512) != ((e & 1024) != 0);
-                    b[h] = neg ? (0ull - val) : val;
-                }
-                own2[m] = uint4{(uint32_t)b[0], (uint32_t)(b[0] >> 32), (uint32_t)b[1], (uint32_t)(b[1] >> 32)};
-                z[m] = uint4{0, 0, 0, 0};
-            }
-            tmem_st_u4x8(tm_own, z);
-            tmem_st_u4x8(tm_own + 32, z);
-            tmem_st_u4x8(tm_own + 64, own2);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        }
-        group_sync(bar);
-        int tile = 0;
-#pragma unroll 1
-        for (int i = 0; i < kLweN; i++) {
-            const int d = rot[i];
-            const bool skip = (d == 0);
-            cplx out[3][8];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int k = 0; k < 8; k++) out[c][k] = cplx{0.0, 0.0};
-#pragma unroll 1
-            for (int r = 0; r < 3; r++, tile++) {
-                const int buf = tile % R;
-                const int use = tile / R;
-                if (producer && tile >= 1 && tile - 1 + R < kTiles) {
-                    const int pb = (tile - 1) % R, puse = (tile - 1) / R;
-                    mbar_wait(empty + pb, puse & 1);
-                    tma_load_tile(ring + pb * kBrTileBytes, bsk_bytes + (size_t)(tile - 1 + R) * kBrTileBytes, kBrTileBytes, full + pb);
-                }
-                __syncwarp();
-                if (!skip) {
-                    cplx v[8];
-                    {
-                        uint4 ownv[8];
-                        tmem_ld_u4x8(tm_own + 32 * r, ownv);
-                        uint4 *stage = reinterpret_cast<uint4 *>(flip ? scr1 : scr0);
-                        flip ^= 1;
-#pragma unroll
-                        for (int m = 0; m < 8; m++) stage[t + 64 * m] = ownv[m];
-                        group_sync(bar);
-#pragma unroll
-                        for (int m = 0; m < 8; m++) {
-                            const int jj = t + 64 * m;
-                            const int e0 = (jj - d) & 2047;
-                            const uint4 src = stage[e0 & 511];
-                            const uint4 own = ownv[m];
-                            const bool sw = (e0 & 512) != 0;
-                            const uint32_t ml = (uint32_t)((int32_t)(e0 << 21) >> 31);
-                            const uint32_t mh = (uint32_t)((int32_t)((e0 ^ (e0 << 1)) << 21) >> 31);
-                            const uint32_t rll = sw ? src.z : src.x, rlh = sw ? src.w : src.y;
-                            const uint32_t rhl = sw ? src.x : src.z, rhh = sw ? src.y : src.w;
-                            v[m] = cplx{digit_b23_l1_double(hi_condneg_sub(rll, rlh, ml, own.x, own.y)),
-                                        digit_b23_l1_double(hi_condneg_sub(rhl, rhh, mh, own.z, own.w))};
-                        }
-                    }
-                    cplx *s = flip ? scr1 : scr0;
-                    flip ^= 1;
-                    fwd_p1_tm(v, s, tm, t);
-                    group_sync(bar);
-                    fwd_p2x_tm(v, s, tm, t);
-                    exchange8<-1>(v, t & 7);
-                    fwd_p3x(v);
-                    const cplx *key = reinterpret_cast<const cplx *>(ring + buf * kBrTileBytes) + t;
-                    mbar_wait(full + buf, use & 1);
-#pragma unroll
-                    for (int c = 0; c < 3; c++)
-#pragma unroll
-                        for (int k3 = 0; k3 < 8; k3++) cfma(out[c][k3], v[k3], key[c * 512 + k3 * 64]);
-                } else {
-                    mbar_wait(full + buf, use & 1);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty + buf);
-            }
-            if (skip) continue;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                cplx *s = flip ? scr1 : scr0;
-                flip ^= 1;
-                inv_p3x(out[c]);
-                exchange8<1>(out[c], t & 7);
-                inv_p2x_tm(out[c], s, tm, t);
-                group_sync(bar);
-                inv_p1_tm(out[c], s, tm, t);
-                uint4 ownv[8];
-                tmem_ld_u4x8(tm_own + 32 * c, ownv);
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const uint64_t lo = (((uint64_t)ownv[m].y << 32) | ownv[m].x) + torus_from_scaled(out[c][m].x);
-                    const uint64_t hi = (((uint64_t)ownv[m].w << 32) | ownv[m].z) + torus_from_scaled(out[c][m].y);
-                    ownv[m] = uint4{(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
-                }
-                tmem_st_u4x8(tm_own + 32 * c, ownv);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        }
-        uint64_t *o = acc_out + (size_t)ct * kGlweWords;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            uint4 ownv[8];
-            tmem_ld_u4x8(tm_own + 32 * c, ownv);
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                o[c * 1024 + t + 64 * m] = ((uint64_t)ownv[m].y << 32) | ownv[m].x;
-                o[c * 1024 + t + 64 * m + 512] = ((uint64_t)ownv[m].w << 32) | ownv[m].z;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc_cols(*tmem_slot, 512);
-}
-
 // Other decompositions measured on B200 and rejected (tools/brbench.py, 1024 ciphertexts):
 //   * one polynomial per 64-thread sub-group, three sub-groups per ciphertext, spectra exchanged through
 //     the transpose tiles (per-step latency 15.9 k -> 9.3 k cycles, but only 2 ciphertexts fit per SM):
@@ -1005,6 +777,25 @@ __global__ void __launch_bounds__(MAXT, 1) k_blind_rotate_v7(const uint64_t *__r
 //     occupancy): 13.7 ms, 136 B of spills;
 //   * pass-2 twiddles in a shared table: 13.3 ms; balancing the last wave with 3-group CTAs: -2 % only,
 //     because a group's step is a latency chain that does not speed up when its neighbours leave.
+// Session 3 of round 2 (all parity-green on B200, code in git history at fbc3b6c, numbers in profiles/r02_brbench_variants.txt):
+//   * the ACCUMULATOR in tensor memory (every thread owns its 24 coefficient pairs in 96 columns, update = LDTM/add/STTM, the
+//     build stages the polynomial through a transient 8 KB tile): 16 instead of 40 KB of shared memory per ciphertext, so
+//     SIX groups per SM (12 warps, 168 registers) and a 3-row key ring fit: 8.30 ms per wave of 888 = 9.34 us per
+//     ciphertext, EXACTLY v4's 5.53 ms per 592; the same kernel at 4 groups 5.73 ms (252 registers) / 6.33 ms (compiled at
+//     the 168-register cap): 8 -> 12 warps buy +14 %, the register cap costs 10 %, the staging barrier 4 %;
+//   * BSK tiles shared memory -> tensor memory with tcgen05.cp (SASS UTCCP, tools/test_utccp.cu) and key reads with
+//     tcgen05.ld: 7.1-7.2 ms per 592 (tensor-memory read bandwidth, 98 KB per tile and CTA);
+//   * the thread's own accumulator coefficients mirrored in tensor memory (-16 % shared-memory wavefronts): 5.61 ms;
+//   * the build of polynomial r + 1 software-pipelined into the products / pass 2 of polynomial r: 5.97 / 6.12 ms with the
+//     rolled loop (one wasted build per step), 7.1 / 6.1 ms unrolled (80 KB of code: stall_no_instruction 0.49 per issue);
+//   * polynomials 0,1 and columns 0,1 transformed as pairs (twiddles fetched once for both): 5.61 ms.
+// Why none of them moves the needle (tools/bench_rf.cu, bench_issue.cu, bench_fp64ops.cu, bench_dft8.cu):
+// the kernel is bound by REGISTER-FILE READ BANDWIDTH.  A scheduler fetches two 32-bit register operands per cycle: DADD/DMUL
+// with two fresh 64-bit sources issue every 2 cycles (the nominal FP64 rate), a DFMA with three every 3.06 cycles, a 3-source
+// LOP3/IMAD every 2; DADD + LOP3 pairs take 3.6 cycles and not 2.  ncu shows 0.53 (8 warps) and 0.56 (12 warps) instructions per
+// cycle and scheduler and the same 55.7 % FP64-pipe utilisation at both occupancies, and 96 extra instructions per step of
+// ANY kind (LOP3 inside the products, LOP3 or DFMA inside the build) cost +1.9 ... +2.5 % each.  tools/sass_rf_model.py counts
+// 10,555 register source words per warp and step (lower bound 5,278 cycles against 3,924 of FP64-pipe time and 7,050 measured).
 // Per-step cycle budget of a group before the twiddles moved to tensor memory (clock64 probes, round 1): build 4.2 k, forward passes 3.3 k, pass 3 + MAC 2.8 k,
 // inverse 4.2 k, torus + update 1.5 k, tile wait 0.5 k.
 // Round 2, all parity-green on B200 and all slower (code in git history, commit 1d4... "Blind rotation experiments";
@@ -1197,10 +988,6 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
     std::call_once(once[dev], [&] {
         cudaFuncSetAttribute(k_blind_rotate_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, kLlSmemBytes);
         cudaFuncSetAttribute(k_blind_rotate_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, kBr4SmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v7<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br7<4>::kSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v7<4, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br7<4>::kSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v7<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br7<5>::kSmemBytes);
-        cudaFuncSetAttribute(k_blind_rotate_v7<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Br7<6>::kSmemBytes);
         int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         sm_count[dev] = n > 0 ? n : 1;
@@ -1221,18 +1008,10 @@ void launch_blind_rotate(const DeviceKeys &K, const uint64_t *lwe, uint64_t *acc
         return;
     }
     // a last partial wave of at most two ciphertexts per SM also goes to the team kernel (3.2 / 2.4 ms instead of 5.8 ms)
-    static const int variant = getenv("CBS_BR_V") ? atoi(getenv("CBS_BR_V")) : 0;
-    const int groups = variant == 12 ? 6 : variant == 11 ? 5 : kBrGroups;
-    const int wave = sms * groups, rem = count % wave;
+    const int wave = sms * kBrGroups, rem = count % wave;
     int head = count;
     if (ll_mode == 1 && count > wave && rem > 0 && rem <= kLlTeams * sms) head = count - rem;
-    switch (variant) {
-    case 10: k_blind_rotate_v7<4><<<(head + 3) / 4, 256, Br7<4>::kSmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw); break;
-    case 13: k_blind_rotate_v7<4, 384><<<(head + 3) / 4, 256, Br7<4>::kSmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw); break;
-    case 11: k_blind_rotate_v7<5><<<(head + 4) / 5, 320, Br7<5>::kSmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw); break;
-    case 12: k_blind_rotate_v7<6><<<(head + 5) / 6, 384, Br7<6>::kSmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw); break;
-    default: k_blind_rotate_v4<<<(head + kBrGroups - 1) / kBrGroups, 64 * kBrGroups, kBr4SmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw);
-    }
+    k_blind_rotate_v4<<<(head + kBrGroups - 1) / kBrGroups, 64 * kBrGroups, kBr4SmemBytes, s>>>(lwe, acc, head, K.bsk_f, K.tw);
     if (head < count) launch_team(lwe + (size_t)head * kLweSmall, acc + (size_t)head * kGlweWords, count - head);
 }
 

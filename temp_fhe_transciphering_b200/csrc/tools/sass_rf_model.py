@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Development tool: register-file read model of a kernel's main loop, from its SASS.
+
+tools/bench_rf.cu measured on B200: a scheduler reads two 32-bit register operands per cycle; a DFMA with three distinct
+64-bit register sources issues every 3.06 cycles (not 2), DADD + LOP3 pairs take 3.6 cycles (2 + 1.5), operands that hit the
+reuse cache or are immediates / uniform registers / constant-bank references are free.  This script walks the loop nest of
+a blind-rotation kernel like sass_loop_count.py and sums, per warp and step,
+  cost(instruction) = max(pipe cycles, register source words / 2)
+with pipe cycles = 2 for FP64, ALU and IMAD instructions and 1 otherwise.
+usage: sass_rf_model.py <object> <mangled kernel name> [inner weight]"""
+import collections
+import re
+import subprocess
+import sys
+
+obj, fun = sys.argv[1], sys.argv[2]
+w_inner = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+out = subprocess.run(["cuobjdump", "-sass", "-fun", fun, obj], capture_output=True, text=True).stdout
+ins = []
+for l in out.splitlines():
+    m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)\s*(.*?);", l)
+    if m:
+        ins.append((int(m.group(1), 16), m.group(3), m.group(4)))
+loops = []
+for a, op, rest in ins:
+    if op.startswith("BRA"):
+        m = re.search(r"0x([0-9a-f]+)", rest)
+        if m and int(m.group(1), 16) <= a:
+            loops.append((int(m.group(1), 16), a))
+fp = [a for a, op, _ in ins if op in ("DADD", "DFMA", "DMUL")]
+big = sorted([l for l in loops if sum(1 for x in fp if l[0] <= x <= l[1]) > 50], key=lambda l: l[0] - l[1])
+outer = big[0]
+inner = [l for l in big[1:] if outer[0] <= l[0] and l[1] <= outer[1]]
+inner = inner[0] if inner else None
+
+HALF = ("DADD", "DFMA", "DMUL", "LOP3", "IADD3", "SEL", "VIADD", "IMAD", "LEA", "SHF", "ISETP", "PLOP3", "PRMT", "IABS", "FLO", "POPC", "F2I", "I2F")
+WIDE = {"DADD": 2, "DFMA": 2, "DMUL": 2, "F2I": 2}
+
+
+def src_words(op, rest, prev_reuse):
+    base = op.split(".")[0]
+    ops = [o.strip() for o in rest.split(",")]
+    if base in ("STS", "STG", "ST", "STL", "STTM", "BAR", "BRA", "SYNCS", "RED", "ATOMS", "EXIT", "NOP", "BSYNC", "BSSY", "WARPSYNC", "ENDCOLLECTIVE",
+                "YIELD", "UBLKCP", "R2UR", "DEPBAR", "ERRBAR", "CCTL", "MEMBAR", "CALL", "RET"):
+        srcs = ops  # no register destination
+    else:
+        srcs = ops[1:]
+        # predicate destinations (P0, PT) in front
+        while srcs and re.match(r"^!?U?P(T|\d+)$", srcs[0]):
+            srcs = srcs[1:]
+    words = 0
+    reuse_now = {}
+    width = WIDE.get(base, 1)
+    for slot, o in enumerate(srcs):
+        regs = re.findall(r"(?<![A-Z])R(\d+)((?:\.[A-Za-z0-9_]+)*)", o)
+        for num, suffix in regs:
+            w = width
+            if base in ("STS", "STG", "STL") and slot == len(srcs) - 1 and not o.startswith("["):
+                w = 4 if ".128" in op else 2 if ".64" in op else 1
+            if base in ("LDS", "LDG", "LDL", "STS", "STG", "STL") and o.startswith("["):
+                w = 1 if base in ("LDS", "STS", "LDL", "STL") else 2
+            if base == "STTM" and not o.startswith("tmem"):
+                w = int(re.search(r"x(\d+)", op).group(1)) if re.search(r"x(\d+)", op) else 1
+            if base == "IMAD" and ".WIDE" in op and slot == 2:
+                w = 2
+            key = (slot, num)
+            if prev_reuse.get(key):
+                w = 0
+            if ".reuse" in suffix:
+                reuse_now[key] = True
+            words += w
+    return words, reuse_now
+
+
+cost = collections.Counter()
+count = collections.Counter()
+reads = collections.Counter()
+prev = {}
+tot_cost = tot_reads = tot_n = 0
+for a, op, rest in ins:
+    if not (outer[0] <= a <= outer[1]):
+        prev = {}
+        continue
+    w = w_inner if inner and inner[0] <= a <= inner[1] else 1
+    words, prev = src_words(op, rest, prev)
+    base = op.split(".")[0]
+    pipe = 2 if base in HALF else 1
+    c = max(pipe, words / 2.0)
+    cost[base] += w * c
+    count[base] += w
+    reads[base] += w * words
+    tot_cost += w * c
+    tot_reads += w * words
+    tot_n += w
+print(f"per warp-step: {tot_n} instructions, {tot_reads} register source words, "
+      f"sum of max(pipe, words / 2) = {tot_cost:.0f} cycles (x warps per scheduler = cycles per step if nothing overlaps)")
+print(f"  lower bounds per warp-step: register file {tot_reads / 2:.0f}, issue slots {tot_n}, FP64 pipe {2 * (count['DADD'] + count['DFMA'] + count['DMUL'])}")
+for k, v in cost.most_common(16):
+    print(f"  {k:10s} n={count[k]:5d} words={reads[k]:6d} cost={v:7.0f}")
