@@ -101,13 +101,16 @@ int ws_get(cbs_ctx *ctx, const char *name, size_t bytes, void **out)
 {
     DevBuf &b = ctx->ws[ctx->lane >= 0 ? std::string("lane") + std::to_string(ctx->lane) + ":" + name : std::string(name)];
     if (b.bytes < bytes) {
+        // stream-ordered growth (no device-wide synchronisation inside a compute call): a workspace is only ever used on
+        // the stream of the lane that owns it, so freeing and re-allocating on that stream orders correctly with its work;
+        // the device's default pool keeps freed blocks (release threshold set in cbs_ctx_create)
+        cudaStream_t st = S(ctx);
         if (b.p) {
-            CUDA_TRY(cudaDeviceSynchronize());
-            CUDA_TRY(cudaFree(b.p));
+            CUDA_TRY(cudaFreeAsync(b.p, st));
             b.p = nullptr;
             b.bytes = 0;
         }
-        CUDA_TRY(cudaMalloc(&b.p, bytes));
+        CUDA_TRY(cudaMallocAsync(&b.p, bytes, st));
         b.bytes = bytes;
     }
     *out = b.p;
@@ -413,10 +416,20 @@ int cbs_device_count(int *count)
     return CBS_OK;
 }
 
+// workspaces come from the stream-ordered allocator (ws_get): keep what it frees cached in the device's default pool
+static void keep_pool_memory(int device)
+{
+    cudaMemPool_t pool = nullptr;
+    uint64_t keep = UINT64_MAX;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaGetLastError();
+}
+
 int cbs_device_init(int device)
 {
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaFree(nullptr));
+    keep_pool_memory(device);
     return CBS_OK;
 }
 
@@ -446,6 +459,7 @@ int cbs_ctx_create(const cbs_keyset *ks, int device, cbs_ctx **out)
     if (const char *e = getenv("CBS_CHUNK_BLOCKS")) ctx->chunk_blocks = std::max(1, atoi(e));
     if (const char *e = getenv("CBS_LANES")) ctx->lanes = std::max(1, std::min((int)cbs_ctx::kMaxLanes, atoi(e)));
     Activate act(ctx);
+    keep_pool_memory(device);
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
