@@ -15,6 +15,13 @@ import sys
 
 obj, fun = sys.argv[1], sys.argv[2]
 w_inner = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+# optional explicit weights for address ranges inside the loops (if/else bodies): "0x3f60-0x4660:1,0x4670-0x4d70:2"
+ranges = []
+if len(sys.argv) > 4:
+    for part in sys.argv[4].split(","):
+        r, wt = part.split(":")
+        lo, hi = r.split("-")
+        ranges.append((int(lo, 16), int(hi, 16), float(wt)))
 out = subprocess.run(["cuobjdump", "-sass", "-fun", fun, obj], capture_output=True, text=True).stdout
 ins = []
 for l in out.splitlines():
@@ -28,10 +35,11 @@ for a, op, rest in ins:
         if m and int(m.group(1), 16) <= a:
             loops.append((int(m.group(1), 16), a))
 fp = [a for a, op, _ in ins if op in ("DADD", "DFMA", "DMUL")]
-big = sorted([l for l in loops if sum(1 for x in fp if l[0] <= x <= l[1]) > 50], key=lambda l: l[0] - l[1])
-outer = big[0]
-inner = [l for l in big[1:] if outer[0] <= l[0] and l[1] <= outer[1]]
-inner = inner[0] if inner else None
+nfp = lambda l: sum(1 for x in fp if l[0] <= x <= l[1])
+big = [l for l in loops if nfp(l) > 50]
+outer = min(big, key=lambda l: l[0])  # the step loop starts first; later "loops" are out-of-line retry paths jumping back
+inner = [l for l in big if l != outer and outer[0] <= l[0] and l[1] <= outer[1]]
+inner = max(inner, key=nfp) if inner else None
 
 HALF = ("DADD", "DFMA", "DMUL", "LOP3", "IADD3", "SEL", "VIADD", "IMAD", "LEA", "SHF", "ISETP", "PLOP3", "PRMT", "IABS", "FLO", "POPC", "F2I", "I2F")
 WIDE = {"DADD": 2, "DFMA": 2, "DMUL": 2, "F2I": 2}
@@ -82,6 +90,9 @@ for a, op, rest in ins:
         prev = {}
         continue
     w = w_inner if inner and inner[0] <= a <= inner[1] else 1
+    for lo, hi, wt in ranges:
+        if lo <= a <= hi:
+            w = wt
     words, prev = src_words(op, rest, prev)
     base = op.split(".")[0]
     pipe = 2 if base in HALF else 1
@@ -92,8 +103,9 @@ for a, op, rest in ins:
     tot_cost += w * c
     tot_reads += w * words
     tot_n += w
+print(f"outer {outer[0]:#x}-{outer[1]:#x} inner {inner and (hex(inner[0]), hex(inner[1]))}")
 print(f"per warp-step: {tot_n} instructions, {tot_reads} register source words, "
       f"sum of max(pipe, words / 2) = {tot_cost:.0f} cycles (x warps per scheduler = cycles per step if nothing overlaps)")
 print(f"  lower bounds per warp-step: register file {tot_reads / 2:.0f}, issue slots {tot_n}, FP64 pipe {2 * (count['DADD'] + count['DFMA'] + count['DMUL'])}")
 for k, v in cost.most_common(16):
-    print(f"  {k:10s} n={count[k]:5d} words={reads[k]:6d} cost={v:7.0f}")
+    print(f"  {k:10s} n={count[k]:7.0f} words={reads[k]:8.0f} cost={v:7.0f}")
