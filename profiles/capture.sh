@@ -26,4 +26,4 @@ ncu --set full --clock-control none --import-source on -k regex:k_trace_v3 -s 2 
 #   python profiles/summarize.py launches gpurun_out/r02_launches.csv FIRST LAST profiles/r02_launch_summary.csv "<comment>"
 #   python profiles/summarize.py full gpurun_out/r02_br_v4_512.ncu-rep profiles/r02_blind_rotate_ncu_full.csv "<comment>"
 #   python profiles/summarize.py full gpurun_out/r02_trace.ncu-rep profiles/r02_trace_ncu_full.csv "<comment>"
-#   cuobjdump -sass temp_fhe_transciphering_b200/libcbs_b200.so | grep -oE '\b(UBLKCP|SYNCS[A-Z.0-9]*|DFMA|DADD|DMUL|SHFL\.IDX|UTMALDG|UTC[A-Z]*MMA|LDTM|STTM|HMMA|DMMA)\b' | sort | uniq -c > profiles/r02_sass_grep.txt
+#   cuobjdump -sass temp_fhe_transciphering_b200/libcbs_b200.so | grep -oE '\b(UBLKCP|SYNCS[A-Z.0-9]*|DFMA|DADD|DMUL|SHFL\.IDX|UTMALDG|UTC[A-Z]*MMA|UTCCP[A-Z.]*|LDTM[.x0-9]*|STTM[.x0-9]*|HMMA|DMMA)\b' | sort | uniq -c > profiles/r02_sass_grep.txt
