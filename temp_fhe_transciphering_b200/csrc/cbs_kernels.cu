@@ -1319,289 +1319,6 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
     if (warp == 0) tmem_dealloc_cols(*tmem_slot, 128);
 }
 
-__device__ __forceinline__ void tmem_ld_u4x8(uint32_t taddr, uint4 w[8])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(w[0].x), "=r"(w[0].y), "=r"(w[0].z), "=r"(w[0].w), "=r"(w[1].x), "=r"(w[1].y), "=r"(w[1].z), "=r"(w[1].w),
-          "=r"(w[2].x), "=r"(w[2].y), "=r"(w[2].z), "=r"(w[2].w), "=r"(w[3].x), "=r"(w[3].y), "=r"(w[3].z), "=r"(w[3].w),
-          "=r"(w[4].x), "=r"(w[4].y), "=r"(w[4].z), "=r"(w[4].w), "=r"(w[5].x), "=r"(w[5].y), "=r"(w[5].z), "=r"(w[5].w),
-          "=r"(w[6].x), "=r"(w[6].y), "=r"(w[6].z), "=r"(w[6].w), "=r"(w[7].x), "=r"(w[7].y), "=r"(w[7].z), "=r"(w[7].w)
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_u4x8(uint32_t taddr, const uint4 w[8])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-        "%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-        "r"(w[0].x), "r"(w[0].y), "r"(w[0].z), "r"(w[0].w), "r"(w[1].x), "r"(w[1].y), "r"(w[1].z), "r"(w[1].w), "r"(w[2].x),
-        "r"(w[2].y), "r"(w[2].z), "r"(w[2].w), "r"(w[3].x), "r"(w[3].y), "r"(w[3].z), "r"(w[3].w), "r"(w[4].x), "r"(w[4].y),
-        "r"(w[4].z), "r"(w[4].w), "r"(w[5].x), "r"(w[5].y), "r"(w[5].z), "r"(w[5].w), "r"(w[6].x), "r"(w[6].y), "r"(w[6].z),
-        "r"(w[6].w), "r"(w[7].x), "r"(w[7].y), "r"(w[7].z), "r"(w[7].w)
-        : "memory");
-}
-
-// k_trace_v5<U, ALIASX, PKTM>: k_trace_v3 with U GLWE units per CTA.  U = 3 (12 warps, 168 registers) fits because the exchange tile is
-// ALIASED onto the sub-group's transpose tile (one more 64-thread barrier per level: every thread of the sub-group must have
-// finished reading the transposed values before the spectrum overwrites them) - 40 instead of 56 KB per unit - and the packed
-// digits of a step (16 x u64 per thread, live across the three levels) are parked in tensor memory (PKTM).
-template <int U, bool ALIASX, bool PKTM>
-__global__ void __launch_bounds__(128 * U, 1) k_trace_v5(const uint64_t *__restrict__ in,
-                                                                 uint64_t *__restrict__ out, int count, int from_acc,
-                                                                 const double *__restrict__ auto_f,
-                                                                 const double *__restrict__ twtab)
-{
-    constexpr int kUnitSmem = kGlweWords * 8 + 2 * 8192 + (ALIASX ? 0 : 2 * 8192);
-    constexpr int kTmCols = (64 + (PKTM ? 32 : 0)) * ((4 * U + 3) / 4) <= 128 ? 128 : (64 + (PKTM ? 32 : 0)) * ((4 * U + 3) / 4) <= 256 ? 256 : 512;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gl = threadIdx.x >> 7;
-    const int sub = (threadIdx.x >> 6) & 1;
-    const int t = threadIdx.x & 63;
-    const int idx = blockIdx.x * U + gl;
-    unsigned char *ring = smem_raw + (size_t)U * kUnitSmem;  // lane (i, limb) at (limb*2 + i) * 24,576
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + 4 * kBrTileBytes + 1024);
-    uint64_t *empty = full + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + 4);
-    const int warp = threadIdx.x >> 5;
-    const int active_units = min(U, count - blockIdx.x * U);
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < 4; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, 64 * active_units);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tmem_alloc_cols(tmem_slot, kTmCols);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // the 16 complex twiddles of a thread live in tensor memory (see k_blind_rotate_v4): 64 columns per warp, the two warps
-    // of a lane quarter side by side
-    const uint32_t tm = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((64 + (PKTM ? 32 : 0)) * (warp >> 2));
-    const uint32_t tm_pk = tm + 64;
-    {
-        Twiddles tw;
-        load_twiddles_x(tw, twtab, t);
-        tmem_st_c4(tm, tw.t1);
-        tmem_st_c4(tm + 16, tw.t1 + 4);
-        tmem_st_c4(tm + 32, tw.t2);
-        tmem_st_c4(tm + 48, tw.t2 + 4);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    if (idx < count) {
-        const bool producer = (threadIdx.x == 0);
-        const char *key_bytes = reinterpret_cast<const char *>(auto_f);
-        // tile of use n = s*3 + tt (level lev = 2 - tt), lane (i, sp): Fourier polys [s][i][sp][lev][0..2]
-        auto tile_src = [&](int n, int i, int sp) {
-            const int s = n / 3, lev = 2 - (n % 3);
-            return key_bytes + (size_t)((((s * 2 + i) * 2 + sp) * 3 + lev) * 3) * kFourierPolyDoubles * 8;
-        };
-        // refill of the four ring lanes for use n: `early` only takes the lanes every consumer has already released
-        // (non-blocking test right after a level's products), the regular call one barrier into the next transform
-        // blocks for the rest.  issued = bit mask of the lanes already requested for the pending use.
-        int issued = 0;
-        auto produce = [&](int n, bool early) {
-            if (n >= 30) return;
-    #pragma unroll
-            for (int L = 0; L < 4; L++) {
-                if (issued & (1 << L)) continue;
-                if (n > 0) {
-                    if (early) {
-                        if (!mbar_test(empty + L, (n - 1) & 1)) continue;
-                    } else {
-                        mbar_wait(empty + L, (n - 1) & 1);
-                    }
-                }
-                tma_load_tile(ring + L * kBrTileBytes, tile_src(n, L & 1, L >> 1), kBrTileBytes, full + L);
-                issued |= 1 << L;
-            }
-            if (!early) issued = 0;
-        };
-        if (producer) produce(0, false);
-        __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-        int want = -1;  // next ring refill the producer owes (issued one barrier into the following transform)
-
-        unsigned char *base = smem_raw + (size_t)gl * kUnitSmem;
-        u64x2 *cur = reinterpret_cast<u64x2 *>(base);
-        cplx *scr = reinterpret_cast<cplx *>(base + kGlweWords * 8 + sub * 8192);
-        // exchange tile [sub 2][512]: its own 16 KB, or (ALIASX) the two transpose tiles of the unit
-        cplx *X = reinterpret_cast<cplx *>(base + kGlweWords * 8 + (ALIASX ? 0 : 16384));
-        const int sbar = 1 + gl * 2 + sub;
-        const int ubar = 1 + 2 * U + gl;
-        {
-            const int u = threadIdx.x & 127;
-            if (from_acc) {
-                const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
-                const int lvl = idx % kCbsLevel;
-                for (int w = u; w < 3 * 512; w += 128) {
-                    const int p = w >> 9, jj = w & 511;
-                    cur[w] = u64x2{glev_pre_word(acc, lvl, p, jj), glev_pre_word(acc, lvl, p, jj + 512)};
-                }
-            } else {
-                const uint64_t *src = in + (size_t)idx * kGlweWords;
-                for (int w = u; w < 3 * 512; w += 128) {
-                    const int p = w >> 9, jj = w & 511;
-                    cur[w] = u64x2{src[p * 1024 + jj], src[p * 1024 + jj + 512]};
-                }
-            }
-        }
-        unit_sync(ubar);
-
-    #pragma unroll 1
-        for (int s = 0; s < 10; s++) {
-            const int kinv = c_kappa_inv[s];
-            uint64_t pk[16];
-            {
-                const u64x2 *p = cur + sub * 512;
-    #pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const int jj = t + 64 * m;
-                    const int e = (jj * kinv) & 2047;
-                    const u64x2 A = p[e & 511];
-                    const int h = e >> 9;
-                    pk[2 * m] = pack_digits<13, 3, uint64_t>(pair_pick(A, h));
-                    pk[2 * m + 1] = pack_digits<13, 3, uint64_t>(pair_pick(A, (h + kinv) & 3));
-                }
-            }
-            if (PKTM) {
-                uint4 w[8];
-    #pragma unroll
-                for (int m = 0; m < 8; m++)
-                    w[m] = uint4{(uint32_t)pk[2 * m], (uint32_t)(pk[2 * m] >> 32), (uint32_t)pk[2 * m + 1], (uint32_t)(pk[2 * m + 1] >> 32)};
-                tmem_st_u4x8(tm_pk, w);
-            }
-            u64x2 nb[4];
-    #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int jj = t + 64 * (4 * sub + q);
-                const int e = (jj * kinv) & 2047;
-                const u64x2 A = cur[1024 + (e & 511)];
-                const int h = e >> 9;
-                const u64x2 own = cur[1024 + jj];
-                nb[q] = u64x2{own.lo + pair_pick(A, h), own.hi + pair_pick(A, (h + kinv) & 3)};
-            }
-            unit_sync(ubar);
-    #pragma unroll
-            for (int q = 0; q < 4; q++) cur[1024 + t + 64 * (4 * sub + q)] = nb[q];
-
-            cplx acc[3][8];
-    #pragma unroll
-            for (int c = 0; c < 3; c++)
-    #pragma unroll
-                for (int k = 0; k < 8; k++) acc[c][k] = cplx{0.0, 0.0};
-    #pragma unroll 1
-            for (int tt = 0; tt < 3; tt++) {
-                const int n = s * 3 + tt;
-                cplx v[8];
-                if (PKTM) {
-                    uint4 w[8];
-                    if (tt == 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tmem_ld_u4x8(tm_pk, w);
-    #pragma unroll
-                    for (int m = 0; m < 8; m++)
-                        v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(((uint64_t)w[m].y << 32) | w[m].x, tt)),
-                                    i32_to_double(unpack_digit<13, uint64_t>(((uint64_t)w[m].w << 32) | w[m].z, tt))};
-                } else {
-    #pragma unroll
-                    for (int m = 0; m < 8; m++)
-                        v[m] = cplx{i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m], tt)),
-                                    i32_to_double(unpack_digit<13, uint64_t>(pk[2 * m + 1], tt))};
-                }
-                fwd_p1_tm(v, scr, tm, t);
-                group_sync(sbar);
-                if (producer && want >= 0) {
-                    produce(want, false);
-                    want = -1;
-                }
-                __syncwarp();  // the producer lane rejoins its warp before the next (aligned) named barrier
-                fwd_p2x_tm(v, scr, tm, t);
-                exchange8<-1>(v, t & 7);
-                fwd_p3x(v);
-                if (ALIASX) group_sync(sbar);  // the sub-group has finished reading its transpose tile
-                cplx *Xw = X + sub * 512 + t;
-                const cplx *Xr = X + (1 - sub) * 512 + t;
-    #pragma unroll
-                for (int k3 = 0; k3 < 8; k3++) Xw[k3 * 64] = v[k3];
-                unit_sync(ubar);
-                // own spectrum x key(i = sub, limb = sub), partner spectrum x key(i = 1 - sub, limb = sub)
-                const int Lown = sub * 2 + sub, Loth = sub * 2 + (1 - sub);
-                mbar_wait(full + Lown, n & 1);
-                {
-                    const cplx *key = reinterpret_cast<const cplx *>(ring + Lown * kBrTileBytes) + t;
-    #pragma unroll
-                    for (int c = 0; c < 3; c++)
-    #pragma unroll
-                        for (int k3 = 0; k3 < 8; k3++) cfma(acc[c][k3], v[k3], key[c * 512 + k3 * 64]);
-                }
-                mbar_arrive(empty + Lown);
-                mbar_wait(full + Loth, n & 1);
-                {
-                    const cplx *key = reinterpret_cast<const cplx *>(ring + Loth * kBrTileBytes) + t;
-    #pragma unroll
-                    for (int k3 = 0; k3 < 8; k3++) {
-                        const cplx o = Xr[k3 * 64];
-    #pragma unroll
-                        for (int c = 0; c < 3; c++) cfma(acc[c][k3], o, key[c * 512 + k3 * 64]);
-                    }
-                }
-                mbar_arrive(empty + Loth);
-                want = n + 1;
-                unit_sync(ubar);  // partner finished reading the exchange tile before it is rewritten
-                if (producer) produce(want, true);  // lanes both units have released are refilled right away
-                __syncwarp();
-            }
-            const int shift = sub ? 41 : 0;
-    #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                inv_p3x(acc[c]);
-                exchange8<1>(acc[c], t & 7);
-                if (producer && want >= 0) {
-                    produce(want, false);
-                    want = -1;
-                }
-                __syncwarp();
-                inv_p2x_tm(acc[c], scr, tm, t);
-                group_sync(sbar);
-                inv_p1_tm(acc[c], scr, tm, t);
-                u64x2 *p = cur + c * 512;
-                if (sub == 0) {
-    #pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        u64x2 w = p[t + 64 * m];
-                        w.lo += torus_from_scaled(acc[c][m].x);
-                        w.hi += torus_from_scaled(acc[c][m].y);
-                        p[t + 64 * m] = w;
-                    }
-                }
-                unit_sync(ubar);
-                if (sub == 1) {
-    #pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        u64x2 w = p[t + 64 * m];
-                        w.lo += torus_from_scaled(acc[c][m].x) << shift;
-                        w.hi += torus_from_scaled(acc[c][m].y) << shift;
-                        p[t + 64 * m] = w;
-                    }
-                }
-            }
-            unit_sync(ubar);
-        }
-        uint64_t *dst = out + (size_t)idx * kGlweWords;
-        for (int w = threadIdx.x & 127; w < 3 * 512; w += 128) {
-            const u64x2 x = cur[w];
-            const int c = w >> 9, jj = w & 511;
-            dst[c * 1024 + jj] = x.lo;
-            dst[c * 1024 + jj + 512] = x.hi;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) tmem_dealloc_cols(*tmem_slot, kTmCols);
-}
-
 // Round 2, measured and rejected (code in git history, "trace v4"): one 64-thread group per GLWE with the six keyswitch
 // accumulators in TENSOR MEMORY (tcgen05.ld/st, one round trip per accumulator and input polynomial, the three digit
 // spectra resident in registers, key tiles regrouped per (in poly, limb, column) as three 8 KB bulk copies on one
@@ -1609,6 +1326,10 @@ __global__ void __launch_bounds__(128 * U, 1) k_trace_v5(const uint64_t *__restr
 // this kernel (0.243 ms per wave of 592 GLWEs against 2 x 0.116 ms per wave of 296; profiles/r02_brbench_variants.txt).
 // Like the blind rotation the trace is not limited by its barriers but by three co-limiting pipes (FP64 35 %, shared
 // memory 59 %, issue 39 %) at 8 warps per SM, which the register file (255 per thread) and shared memory pin.
+// Session 3: THREE units per CTA (12 warps at 168 registers; the exchange tile aliased onto the transpose tiles with one
+// more sub-group barrier per level, the packed digits of a step parked in tensor memory, 124 B of spills): parity-green,
+// trace + scheme switch of 512 ciphertexts 1.88 ms against 1.80 ms (2.12 ms without the digits in tensor memory); the
+// aliasing alone costs 0.5 % at two units (profiles/r02_brbench_variants.txt).  More resident warps do not help here either.
 void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int count, int from_acc, cudaStream_t s)
 {
     if (count <= 0) return;
@@ -1628,23 +1349,6 @@ void launch_trace(const DeviceKeys &K, const uint64_t *in, uint64_t *out, int co
         cudaMemcpyToSymbol(c_kappa_inv, kinv, sizeof(kinv));
         cudaFuncSetAttribute(k_trace_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTr3SmemBytes);
         init = true;
-    }
-    static const int variant = getenv("CBS_TR_V") ? atoi(getenv("CBS_TR_V")) : 0;
-    auto smem5 = [](int U, bool alias) { return U * (kGlweWords * 8 + 2 * 8192 + (alias ? 0 : 2 * 8192)) + 4 * kBrTileBytes + 1024 + 64; };
-    if (variant) {
-        static bool attr5[64] = {false};
-        if (!attr5[init_dev & 63]) {
-            cudaFuncSetAttribute(k_trace_v5<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5(3, true));
-            cudaFuncSetAttribute(k_trace_v5<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5(3, true));
-            cudaFuncSetAttribute(k_trace_v5<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5(2, true));
-            cudaFuncSetAttribute(k_trace_v5<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5(2, false));
-            attr5[init_dev & 63] = true;
-        }
-        if (variant == 1) k_trace_v5<3, true, true><<<(count + 2) / 3, 384, smem5(3, true), s>>>(in, out, count, from_acc, K.auto_f, K.tw);
-        if (variant == 2) k_trace_v5<3, true, false><<<(count + 2) / 3, 384, smem5(3, true), s>>>(in, out, count, from_acc, K.auto_f, K.tw);
-        if (variant == 3) k_trace_v5<2, true, false><<<(count + 1) / 2, 256, smem5(2, true), s>>>(in, out, count, from_acc, K.auto_f, K.tw);
-        if (variant == 4) k_trace_v5<2, false, true><<<(count + 1) / 2, 256, smem5(2, false), s>>>(in, out, count, from_acc, K.auto_f, K.tw);
-        return;
     }
     k_trace_v3<<<(count + kTr2Glwe - 1) / kTr2Glwe, 128 * kTr2Glwe, kTr3SmemBytes, s>>>(in, out, count, from_acc, K.auto_f, K.tw);
 }
