@@ -151,77 +151,117 @@ void launch_std_to_fourier(const uint64_t *in, double *out, int npoly, int mode,
 }
 
 // ------------------------------------------------------------------------------------------------
-// 128-point transform for the keyswitch ring N' = 256: batched radix-2 in shared memory,
-// DIF forward (natural -> bit reversed), DIT inverse.  tw128 layout: [128] twist exp(i*pi*j/256),
-// then [64] w = exp(-2*pi*i*j/128).
+// 128-point transform for the keyswitch ring N' = 256 as two register passes over shared memory:
+//   A : radix 8 over the stride-16 points n = j + 16 m of a thread j < 16, twiddle W128^(j k), output y_k[j]
+//   BC: radix 16 over the 16 contiguous values y_k[0..15] of a thread k < 8 (two DFT-8 + one butterfly level)
+// X[k + 8 g] = sum_j W16^(j g) W128^(j k) sum_m x[j + 16 m] W8^(m k) ends up at position ks_pos(k, g); the inverse mirrors
+// it (unnormalised; the key carries the 1/128).  Positions are XOR-swizzled inside each block of 16 so that both passes
+// read and write shared memory without bank conflicts; data and key use the same order, so pointwise products do not care.
+// (Round 1 ran seven radix-2 shared-memory stages: 14 CTA barriers per keyswitch, shared-memory pipe 65 % with 3.1 M bank
+// conflicts, 42 us per 512 ciphertexts.)  tw128 layout: [128] twist exp(i*pi*j/256), then [64] w = exp(-2*pi*i*j/128).
 constexpr int kKsThreads = 256;
+constexpr int kKsCt = 2;  // ciphertexts per CTA: they share every key value fetched from L2
 
-__device__ __forceinline__ void fft128_fwd_batch(cplx *data, int narr, const cplx *w)
+__device__ __forceinline__ int ks_pos(int k, int j) { return 16 * k + (j ^ k); }
+__device__ __forceinline__ cplx ks_w128(const cplx *w, int e)  // exp(-2*pi*i*e/128), 0 <= e < 128
 {
-    for (int len = 128; len >= 2; len >>= 1) {
-        const int half = len >> 1, step = 128 / len;
-        for (int id = threadIdx.x; id < narr * 64; id += kKsThreads) {
-            const int arr = id >> 6, b = id & 63;
-            const int blk = b / half, j = b - blk * half;
-            cplx *base = data + arr * 128 + blk * len;
-            cplx u = base[j], x = base[j + half];
-            base[j] = cadd(u, x);
-            base[j + half] = cmul(csub(u, x), w[j * step]);
-        }
-        __syncthreads();
+    const cplx r = w[e & 63];
+    return (e & 64) ? cplx{-r.x, -r.y} : r;
+}
+__device__ __forceinline__ void ks_fwd_a(cplx v[8], cplx *F, int j, const cplx *w)
+{
+    dft8<false>(v);
+    F[ks_pos(0, j)] = v[0];
+#pragma unroll
+    for (int k = 1; k < 8; k++) F[ks_pos(k, j)] = cmul(v[k], ks_w128(w, j * k));
+}
+__device__ __forceinline__ void ks_fwd_bc(cplx *F, int k, const cplx *w)
+{
+    cplx e[8], o[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        e[a] = F[ks_pos(k, 2 * a)];
+        o[a] = F[ks_pos(k, 2 * a + 1)];
+    }
+    dft8<false>(e);
+    dft8<false>(o);
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        const cplx t = g ? cmul(o[g], w[8 * g]) : o[0];
+        F[ks_pos(k, g)] = cadd(e[g], t);
+        F[ks_pos(k, g + 8)] = csub(e[g], t);
     }
 }
-
-__device__ __forceinline__ void fft128_inv_batch(cplx *data, int narr, const cplx *w)
+__device__ __forceinline__ void ks_inv_bc(cplx *F, int k, const cplx *w)
 {
-    for (int len = 2; len <= 128; len <<= 1) {
-        const int half = len >> 1, step = 128 / len;
-        for (int id = threadIdx.x; id < narr * 64; id += kKsThreads) {
-            const int arr = id >> 6, b = id & 63;
-            const int blk = b / half, j = b - blk * half;
-            cplx *base = data + arr * 128 + blk * len;
-            cplx u = base[j], x = cmul_conj(base[j + half], w[j * step]);
-            base[j] = cadd(u, x);
-            base[j + half] = csub(u, x);
-        }
-        __syncthreads();
+    cplx e[8], o[8];
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        const cplx z0 = F[ks_pos(k, g)], z1 = F[ks_pos(k, g + 8)];
+        e[g] = cadd(z0, z1);
+        o[g] = g ? cmul_conj(csub(z0, z1), w[8 * g]) : csub(z0, z1);
+    }
+    dft8<true>(e);
+    dft8<true>(o);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        F[ks_pos(k, 2 * a)] = e[a];
+        F[ks_pos(k, 2 * a + 1)] = o[a];
     }
 }
-
-__global__ void __launch_bounds__(kKsThreads) k_ksk_to_fourier(const uint64_t *__restrict__ in,
-                                                                double *__restrict__ out, int npoly,
-                                                                const double *__restrict__ tw128)
+__device__ __forceinline__ void ks_inv_a(cplx v[8], const cplx *F, int j, const cplx *w)
 {
-    __shared__ cplx data[128];
-    __shared__ cplx twist[128];
-    __shared__ cplx w[64];
+    v[0] = F[ks_pos(0, j)];
+#pragma unroll
+    for (int k = 1; k < 8; k++) v[k] = cmul_conj(F[ks_pos(k, j)], ks_w128(w, j * k));
+    dft8<true>(v);  // v[m] = 128 x[j + 16 m]
+}
+
+// key polynomial -> Fourier, in the position order of the passes above, scaled by 1/128
+__global__ void __launch_bounds__(128) k_ksk_to_fourier(const uint64_t *__restrict__ in, double *__restrict__ out, int npoly,
+                                                         const double *__restrict__ tw128)
+{
+    __shared__ __align__(16) cplx data[128];
+    __shared__ __align__(16) cplx w[64];
     const int poly = blockIdx.x;
     if (poly >= npoly) return;
-    for (int i = threadIdx.x; i < 128; i += kKsThreads) twist[i] = cplx{tw128[2 * i], tw128[2 * i + 1]};
-    for (int i = threadIdx.x; i < 64; i += kKsThreads) w[i] = cplx{tw128[256 + 2 * i], tw128[256 + 2 * i + 1]};
+    for (int i = threadIdx.x; i < 64; i += 128) w[i] = cplx{tw128[256 + 2 * i], tw128[256 + 2 * i + 1]};
     __syncthreads();
     const uint64_t *p = in + (size_t)poly * 256;
-    for (int j = threadIdx.x; j < 128; j += kKsThreads)
-        data[j] = cmul(cplx{torus_to_double(p[j]), torus_to_double(p[j + 128])}, twist[j]);
-    __syncthreads();
-    fft128_fwd_batch(data, 1, w);
-    for (int j = threadIdx.x; j < 128; j += kKsThreads) {
-        out[((size_t)poly * 128 + j) * 2] = data[j].x * (1.0 / 128.0);
-        out[((size_t)poly * 128 + j) * 2 + 1] = data[j].y * (1.0 / 128.0);
+    if (threadIdx.x < 16) {
+        const int j = threadIdx.x;
+        cplx v[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int n = j + 16 * m;
+            v[m] = cmul(cplx{torus_to_double(p[n]), torus_to_double(p[n + 128])}, cplx{tw128[2 * n], tw128[2 * n + 1]});
+        }
+        ks_fwd_a(v, data, j, w);
     }
+    __syncthreads();
+    if (threadIdx.x < 8) ks_fwd_bc(data, threadIdx.x, w);
+    __syncthreads();
+    const int q = threadIdx.x;
+    out[((size_t)poly * 128 + q) * 2] = data[q].x * (1.0 / 128.0);
+    out[((size_t)poly * 128 + q) * 2 + 1] = data[q].y * (1.0 / 128.0);
 }
 
 void launch_ksk_to_fourier(const uint64_t *in, double *out, int npoly, const double *tw128, cudaStream_t s)
 {
-    k_ksk_to_fourier<<<npoly, kKsThreads, 0, s>>>(in, out, npoly, tw128);
+    k_ksk_to_fourier<<<npoly, 128, 0, s>>>(in, out, npoly, tw128);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2: keyswitch_lwe_ciphertext_by_glwe_keyswitch, cbs_lib/src/fourier_glwe_keyswitch.rs:344-379
 // (convert_lwe_to_glwe_const glwe_conv.rs:12-44 -> keyswitch_glwe_ciphertext :213-342, Vanilla FFT,
-// B = 2^4, l = 3, ring N' = 256 -> sample extract 0).  One CTA per ciphertext; the 24 digit
-// polynomials are transformed together so a whole keyswitch needs 14 CTA barriers.
-constexpr int kKsSmemBytes = (24 * 128 + 128 + 64) * (int)sizeof(cplx);
+// B = 2^4, l = 3, ring N' = 256 -> sample extract 0).  Two ciphertexts per CTA, 3 CTA barriers per keyswitch:
+//   1. thread (ciphertext, input poly i, j): loads its 16 coefficients of the const-embedded input, decomposes them,
+//      and runs pass A of the three digit polynomials straight from registers;
+//   2. pass BC of the 48 digit polynomials (384 sixteen-point jobs);
+//   3. thread (ciphertext, position): the 24 x 4 products against the Fourier key - every key value fetched from L2
+//      serves both ciphertexts of the CTA (round 1: one ciphertext per CTA, 196 KB of key per ciphertext);
+//   4. inverse passes of the 8 output polynomials, untwist, torus rounding, sample extraction.
+constexpr int kKsSmemBytes = (kKsCt * 24 * 128 + 128 + 64) * (int)sizeof(cplx);
 
 __global__ void __launch_bounds__(kKsThreads) k_lwe_keyswitch(const uint64_t *__restrict__ in,
                                                                uint64_t *__restrict__ out, int count,
@@ -229,63 +269,100 @@ __global__ void __launch_bounds__(kKsThreads) k_lwe_keyswitch(const uint64_t *__
                                                                const double *__restrict__ tw128)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx *F = reinterpret_cast<cplx *>(smem_raw);  // [24][128]
-    cplx *twist = F + 24 * 128;
+    cplx *F = reinterpret_cast<cplx *>(smem_raw);  // [ciphertext][24][128]
+    cplx *twist = F + kKsCt * 24 * 128;
     cplx *w = twist + 128;
-    const int ct = blockIdx.x;
-    if (ct >= count) return;
-    const uint64_t *a = in + (size_t)ct * kLweBig;
+    const int ct0 = blockIdx.x * kKsCt;
     for (int i = threadIdx.x; i < 128; i += kKsThreads) twist[i] = cplx{tw128[2 * i], tw128[2 * i + 1]};
     for (int i = threadIdx.x; i < 64; i += kKsThreads) w[i] = cplx{tw128[256 + 2 * i], tw128[256 + 2 * i + 1]};
     __syncthreads();
-    // digits of the const-embedded input, folded + twisted
-    for (int id = threadIdx.x; id < 8 * 128; id += kKsThreads) {
-        const int i = id >> 7, j = id & 127;
-        // const embed: g[0] = a[0], g[j] = -a[256 - j]
-        uint64_t lo = (j == 0) ? a[i * 256] : (0ull - a[i * 256 + 256 - j]);
-        uint64_t hi = 0ull - a[i * 256 + 128 - j];  // coefficient j + 128 -> -a[256 - (j+128)]
-        uint64_t sl = decomp_init(lo, 4, 3), sh = decomp_init(hi, 4, 3);
+    // 1. digits of the const-embedded input (g[0] = a[0], g[n] = -a[256 - n]), folded + twisted, pass A
+    {
+        const int c = threadIdx.x >> 7, i = (threadIdx.x >> 4) & 7, j = threadIdx.x & 15;
+        if (ct0 + c < count) {
+            const uint64_t *a = in + (size_t)(ct0 + c) * kLweBig + i * 256;
+            uint64_t sl[8], sh[8];
 #pragma unroll
-        for (int tt = 0; tt < 3; tt++) {
-            double dl = (double)decomp_next(sl, 4), dh = (double)decomp_next(sh, 4);
-            F[(i * 3 + tt) * 128 + j] = cmul(cplx{dl, dh}, twist[j]);
-        }
-    }
-    __syncthreads();
-    fft128_fwd_batch(F, 24, w);
-    // pointwise multiply-accumulate: 4 output polys x 128 bins
-    cplx acc[2];
-    for (int q = 0; q < 2; q++) {
-        const int id = threadIdx.x + q * kKsThreads;  // 0..511
-        const int c = id >> 7, j = id & 127;
-        cplx s = {0.0, 0.0};
-        for (int i = 0; i < 8; i++) {
+            for (int m = 0; m < 8; m++) {
+                const int n = j + 16 * m;
+                const uint64_t lo = (n == 0) ? a[0] : (0ull - a[256 - n]);
+                const uint64_t hi = 0ull - a[128 - n];  // coefficient n + 128
+                sl[m] = decomp_init(lo, 4, 3);
+                sh[m] = decomp_init(hi, 4, 3);
+            }
 #pragma unroll
             for (int tt = 0; tt < 3; tt++) {
-                const int lev = 2 - tt;
-                cplx k = ldg_cplx(ksk_f + ((size_t)((i * 3 + lev) * 4 + c) * 128 + j) * 2);
-                cfma(s, F[(i * 3 + tt) * 128 + j], k);
+                cplx v[8];
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const double dl = (double)decomp_next(sl[m], 4), dh = (double)decomp_next(sh[m], 4);
+                    v[m] = cmul(cplx{dl, dh}, twist[j + 16 * m]);
+                }
+                ks_fwd_a(v, F + (c * 24 + i * 3 + tt) * 128, j, w);
             }
         }
-        acc[q] = s;
     }
     __syncthreads();
-    for (int q = 0; q < 2; q++) F[threadIdx.x + q * kKsThreads] = acc[q];  // O[c][j] at F[c*128 + j]
+    // 2. pass BC of every digit polynomial
+    for (int id = threadIdx.x; id < kKsCt * 24 * 8; id += kKsThreads) {
+        const int poly = id >> 3, k = id & 7;
+        if (ct0 + poly / 24 < count) ks_fwd_bc(F + poly * 128, k, w);
+    }
     __syncthreads();
-    fft128_inv_batch(F, 4, w);
-    // untwist, round to the torus, sample-extract coefficient 0
-    uint64_t *o = out + (size_t)ct * kLweSmall;
-    for (int id = threadIdx.x; id < 4 * 128; id += kKsThreads) {
-        const int c = id >> 7, j = id & 127;
-        cplx z = cmul_conj(F[c * 128 + j], twist[j]);
-        uint64_t lo = torus_from_scaled(z.x), hi = torus_from_scaled(z.y);
-        if (c < 3) {
-            // lwe[c*256 + x] = m[0] for x = 0, -m[256 - x] otherwise
-            if (j == 0) o[c * 256] = lo;
-            else o[c * 256 + 256 - j] = 0ull - lo;
-            o[c * 256 + 128 - j] = 0ull - hi;
-        } else if (j == 0) {
-            o[kLweN] = lo + a[kBigN];
+    // 3. products: thread (ciphertext c, position q), 4 output polynomials
+    cplx acc[4];
+    {
+        const int c = threadIdx.x >> 7, q = threadIdx.x & 127;
+#pragma unroll
+        for (int o = 0; o < 4; o++) acc[o] = cplx{0.0, 0.0};
+        if (ct0 + c < count) {
+            const cplx *Fc = F + c * 24 * 128 + q;
+#pragma unroll 2
+            for (int i = 0; i < 8; i++) {  // 24 key loads (L2) in flight per thread
+#pragma unroll
+                for (int tt = 0; tt < 3; tt++) {
+                    const int lev = 2 - tt;
+                    const cplx f = Fc[(i * 3 + tt) * 128];
+                    const double *kp = ksk_f + ((size_t)((i * 3 + lev) * 4) * 128 + q) * 2;
+#pragma unroll
+                    for (int o = 0; o < 4; o++) cfma(acc[o], f, ldg_cplx(kp + (size_t)o * 256));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int c = threadIdx.x >> 7, q = threadIdx.x & 127;
+#pragma unroll
+        for (int o = 0; o < 4; o++) F[(c * 24 + o) * 128 + q] = acc[o];  // output polynomial o of ciphertext c
+    }
+    __syncthreads();
+    // 4. inverse passes, untwist, round to the torus, sample-extract coefficient 0
+    if (threadIdx.x < kKsCt * 4 * 8) {
+        const int c = threadIdx.x >> 5, o = (threadIdx.x >> 3) & 3, k = threadIdx.x & 7;
+        if (ct0 + c < count) ks_inv_bc(F + (c * 24 + o) * 128, k, w);
+    }
+    __syncthreads();
+    if (threadIdx.x < kKsCt * 4 * 16) {
+        const int c = threadIdx.x >> 6, o = (threadIdx.x >> 4) & 3, j = threadIdx.x & 15;
+        if (ct0 + c < count) {
+            cplx v[8];
+            ks_inv_a(v, F + (c * 24 + o) * 128, j, w);
+            uint64_t *dst = out + (size_t)(ct0 + c) * kLweSmall;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int n = j + 16 * m;
+                const cplx z = cmul_conj(v[m], twist[n]);
+                const uint64_t lo = torus_from_scaled(z.x), hi = torus_from_scaled(z.y);
+                if (o < 3) {
+                    // lwe[o*256 + x] = m[0] for x = 0, -m[256 - x] otherwise
+                    if (n == 0) dst[o * 256] = lo;
+                    else dst[o * 256 + 256 - n] = 0ull - lo;
+                    dst[o * 256 + 128 - n] = 0ull - hi;
+                } else if (n == 0) {
+                    dst[kLweN] = lo + in[(size_t)(ct0 + c) * kLweBig + kBigN];
+                }
+            }
         }
     }
 }
@@ -301,7 +378,7 @@ void launch_lwe_keyswitch(const DeviceKeys &K, const uint64_t *in, uint64_t *out
         cudaFuncSetAttribute(k_lwe_keyswitch, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsSmemBytes);
         attr = true;
     }
-    k_lwe_keyswitch<<<count, kKsThreads, kKsSmemBytes, s>>>(in, out, count, K.ksk_f, K.tw128);
+    k_lwe_keyswitch<<<(count + kKsCt - 1) / kKsCt, kKsThreads, kKsSmemBytes, s>>>(in, out, count, K.ksk_f, K.tw128);
 }
 
 // ------------------------------------------------------------------------------------------------
