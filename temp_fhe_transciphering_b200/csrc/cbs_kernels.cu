@@ -1248,14 +1248,19 @@ __global__ void __launch_bounds__(128 * kTr2Glwe, 1) k_trace_v3(const uint64_t *
             if (from_acc) {
                 const uint64_t *acc = in + (size_t)(idx / kCbsLevel) * kGlweWords;
                 const int lvl = idx % kCbsLevel;
-                for (int w = u; w < 3 * 512; w += 128) {
-                    const int p = w >> 9, jj = w & 511;
+                // unrolled: the 16 loads of a thread are in flight together and the polynomial index is a constant per iteration
+#pragma unroll
+                for (int it = 0; it < 12; it++) {
+                    const int w = u + 128 * it;
+                    const int p = it >> 2, jj = w & 511;
                     cur[w] = u64x2{glev_pre_word(acc, lvl, p, jj), glev_pre_word(acc, lvl, p, jj + 512)};
                 }
             } else {
                 const uint64_t *src = in + (size_t)idx * kGlweWords;
-                for (int w = u; w < 3 * 512; w += 128) {
-                    const int p = w >> 9, jj = w & 511;
+#pragma unroll
+                for (int it = 0; it < 12; it++) {
+                    const int w = u + 128 * it;
+                    const int p = it >> 2, jj = w & 511;
                     cur[w] = u64x2{src[p * 1024 + jj], src[p * 1024 + jj + 512]};
                 }
             }
@@ -1505,11 +1510,21 @@ __global__ void __launch_bounds__(64 * kSsGroups, 1) k_scheme_switch_v2(const ui
     g.scr0 = reinterpret_cast<cplx *>(base + kGlweWords * 8);
     g.scr1 = g.scr0 + 512;
     g.flip = 0;
-    Twiddles tw;
-    load_twiddles(tw, twtab, g.t);
     const int t = g.t;
     const uint64_t *src = glev + (size_t)idx * kGlweWords;
-    for (int w = t; w < kGlweWords; w += 64) gl[w] = src[w];
+    {
+        // all 24 16-byte loads of a thread in flight at once: the rolled 8-byte loop left 21 % of the kernel's samples on this
+        // prologue (ncu r02, long scoreboard) - a CTA only lives for ~55 us
+        const ulonglong2 *src2 = reinterpret_cast<const ulonglong2 *>(src);
+        ulonglong2 *gl2 = reinterpret_cast<ulonglong2 *>(gl);
+        ulonglong2 buf[kGlweWords / 128];
+#pragma unroll
+        for (int q = 0; q < kGlweWords / 128; q++) buf[q] = src2[t + 64 * q];
+#pragma unroll
+        for (int q = 0; q < kGlweWords / 128; q++) gl2[t + 64 * q] = buf[q];
+    }
+    Twiddles tw;
+    load_twiddles(tw, twtab, g.t);
     group_sync(g.bar);
     // GGSW layout [level][row][poly]; idx = ct*7 + level
     uint64_t *std_base = ggsw_std ? ggsw_std + (size_t)idx * 3 * kGlweWords : nullptr;
