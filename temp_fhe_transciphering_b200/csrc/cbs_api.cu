@@ -59,6 +59,11 @@ struct cbs_ctx {
     cudaStream_t side[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
     int jobs_nblocks[kMaxLanes + 1] = {-1, -1, -1, -1, -1};
+    // end-to-end calls upload the round 8..0 LUTs (26 MB) on a copy stream while the first rounds and the first blind
+    // rotation already run; the first LUT launch of every lane waits for ev_keys
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_keys = nullptr, ev_copy_after = nullptr;
+    bool keys_in_flight = false;
 };
 
 namespace {
@@ -268,6 +273,7 @@ int dev_transcipher_part(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d_
         TRY(dev_keyswitch(ctx, d_st, d_ks, B));
         TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
         const uint64_t *luts = ctx->d_k8_1 + (size_t)(round - 1) * 4 * 16 * 2 * kGlweWords;
+        if (ctx->keys_in_flight && round == 8) CUDA_TRY(cudaStreamWaitEvent(S(ctx), ctx->ev_keys, 0));
         launch_lut8(ctx->K, d_ggsw_f, luts, lut32, out32, d_t4, nb * 16 * 8, 8, ctx->inv_luts_trivial, S(ctx));
         launch_inv_linear(d_t4, d_st, nb, S(ctx));
         ctx->launches += 2;
@@ -581,6 +587,9 @@ void cbs_ctx_destroy(cbs_ctx *ctx)
     if (ctx->d_k10_9) cudaFree(ctx->d_k10_9);
     if (ctx->d_k8_1) cudaFree(ctx->d_k8_1);
     if (ctx->d_k0) cudaFree(ctx->d_k0);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_keys) cudaEventDestroy(ctx->ev_keys);
+    if (ctx->ev_copy_after) cudaEventDestroy(ctx->ev_copy_after);
     if (ctx->d_kf_first) cudaFree(ctx->d_kf_first);
     if (ctx->d_kf_mid) cudaFree(ctx->d_kf_mid);
     if (ctx->d_kf_last) cudaFree(ctx->d_kf_last);
@@ -887,13 +896,39 @@ int cbs_aes128_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const u
     ENTER(ctx);
     if (nblocks < 0 || (nblocks && (!ct || !out)) || !k10_9 || !k8_1 || !k0) return set_error("cbs_aes128_transcipher: bad argument"), CBS_ERR_ARG;
     if (!nblocks) return CBS_OK;
-    TRY(cbs_trans_key_upload(ctx, k10_9, k8_1, k0));
+    // keys: rounds 10 + 9 need k10_9 (3 MB, on the compute stream); k8_1 and k0 (26 MB) are first read by the LUT ladders of
+    // round 8, one keyswitch + blind rotation (>= 2.4 ms) into the call, so they travel on the copy stream meanwhile
+    if (!ctx->d_k10_9) CUDA_TRY(cudaMalloc(&ctx->d_k10_9, (size_t)CBS_K10_9_WORDS * 8));
+    if (!ctx->d_k8_1) CUDA_TRY(cudaMalloc(&ctx->d_k8_1, (size_t)CBS_K8_1_WORDS * 8));
+    if (!ctx->d_k0) CUDA_TRY(cudaMalloc(&ctx->d_k0, (size_t)CBS_K0_WORDS * 8));
+    if (!ctx->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_keys, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copy_after, cudaEventDisableTiming));
+    }
+    // the copy must not overtake earlier work on the compute stream that may still read the old keys
+    CUDA_TRY(cudaEventRecord(ctx->ev_copy_after, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_after, 0));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_k8_1, k8_1, (size_t)CBS_K8_1_WORDS * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_k0, k0, (size_t)CBS_K0_WORDS * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev_keys, ctx->copy_stream));
+    TRY(upload(ctx, ctx->d_k10_9, k10_9, (size_t)CBS_K10_9_WORDS * 8));
     uint8_t *d_ct;
     uint64_t *d_out;
     TRY(ws_typed(ctx, "io_ct", (size_t)nblocks * 16, &d_ct));
     TRY(ws_typed(ctx, "io_result", (size_t)nblocks * 128 * kLweBig, &d_out));
     TRY(upload(ctx, d_ct, ct, (size_t)nblocks * 16));
-    TRY(dev_transcipher(ctx, d_ct, nblocks, d_out));
+    ctx->inv_luts_trivial = all_masks_zero(k8_1, 8 * 4 * 16 * 2) && all_masks_zero(k0, 16 * 2);  // host scan, copies in flight
+    ctx->have_trans_key = true;
+    ctx->keys_in_flight = true;
+    int rc = dev_transcipher(ctx, d_ct, nblocks, d_out);
+    // whatever happened, the compute stream is ordered after the key copy before the call returns (host buffers, later calls)
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_keys, 0);
+    ctx->keys_in_flight = false;
+    if (rc != CBS_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
     return download(ctx, out, d_out, (size_t)nblocks * 128 * kLweBig * 8);
 }
 
