@@ -45,7 +45,8 @@ struct cbs_ctx {
     bool have_fwd_key = false;
     // every mask word of the round 8..1 / round 0 LUTs is zero (always true for AllRdKeys written by the
     // reference, src/data_struct.rs:145-151,258-263); checked at upload, enables the first-CMux shortcut
-    int inv_luts_trivial = 0, fwd_luts_trivial = 0;
+    int inv_luts_trivial = 0, fwd_luts_trivial = 0;  // host-side promise (unused since the device flags below)
+    int *d_masks_nonzero = nullptr;                  // [0] round 8..0 LUTs, [1] forward (CTR) LUTs: 0 = every mask word is zero
     int jobs24_nblocks[5] = {-1, -1, -1, -1, -1};
     std::map<std::string, DevBuf> ws;
     // cached LUT job tables, keyed by block count
@@ -67,18 +68,6 @@ struct cbs_ctx {
 };
 
 namespace {
-
-// true if every GLWE in `luts` (count x 3072 words) has all-zero mask polynomials
-int all_masks_zero(const uint64_t *luts, size_t count)
-{
-    for (size_t g = 0; g < count; g++) {
-        const uint64_t *m = luts + g * kGlweWords;
-        uint64_t acc = 0;
-        for (int j = 0; j < 2048; j++) acc |= m[j];
-        if (acc) return 0;
-    }
-    return 1;
-}
 
 #define CUDA_TRY(expr)                                                                                   \
     do {                                                                                                 \
@@ -274,7 +263,7 @@ int dev_transcipher_part(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d_
         TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
         const uint64_t *luts = ctx->d_k8_1 + (size_t)(round - 1) * 4 * 16 * 2 * kGlweWords;
         if (ctx->keys_in_flight && round == 8) CUDA_TRY(cudaStreamWaitEvent(S(ctx), ctx->ev_keys, 0));
-        launch_lut8(ctx->K, d_ggsw_f, luts, lut32, out32, d_t4, nb * 16 * 8, 8, ctx->inv_luts_trivial, S(ctx));
+        launch_lut8(ctx->K, d_ggsw_f, luts, lut32, out32, d_t4, nb * 16 * 8, 8, ctx->inv_luts_trivial, ctx->d_masks_nonzero, S(ctx));
         launch_inv_linear(d_t4, d_st, nb, S(ctx));
         ctx->launches += 2;
         TRY(check_launch("round"));
@@ -282,7 +271,7 @@ int dev_transcipher_part(cbs_ctx *ctx, const uint8_t *d_ct, int nb, uint64_t *d_
     // last round (:166-180) + per-byte bit reversal (:182-189)
     TRY(dev_keyswitch(ctx, d_st, d_ks, B));
     TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
-    launch_lut8(ctx->K, d_ggsw_f, ctx->d_k0, lut8, out8, d_st, nb * 16 * 2, 2, ctx->inv_luts_trivial, S(ctx));
+    launch_lut8(ctx->K, d_ggsw_f, ctx->d_k0, lut8, out8, d_st, nb * 16 * 2, 2, ctx->inv_luts_trivial, ctx->d_masks_nonzero, S(ctx));
     launch_reverse_bits(d_st, d_out, nb, S(ctx));
     ctx->launches += 2;
     return check_launch("last round");
@@ -327,14 +316,14 @@ int dev_ctr_part(cbs_ctx *ctx, const uint8_t *d_ctr, const uint8_t *d_ct, int nb
         TRY(dev_keyswitch(ctx, d_st, d_ks, B));
         TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
         const uint64_t *luts = ctx->d_kf_mid + (size_t)(round - 2) * 3 * 16 * 2 * kGlweWords;
-        launch_lut8(ctx->K, d_ggsw_f, luts, lut24, out24, d_t3, j24, 6, ctx->fwd_luts_trivial, S(ctx));
+        launch_lut8(ctx->K, d_ggsw_f, luts, lut24, out24, d_t3, j24, 6, ctx->fwd_luts_trivial, ctx->d_masks_nonzero + 1, S(ctx));
         launch_fwd_linear(d_t3, d_st, nb, S(ctx));
         ctx->launches += 2;
         TRY(check_launch("ctr round"));
     }
     TRY(dev_keyswitch(ctx, d_st, d_ks, B));
     TRY(dev_circuit_bootstrap(ctx, d_ks, nullptr, d_ggsw_f, B));
-    launch_lut8(ctx->K, d_ggsw_f, ctx->d_kf_last, lut8, out8, d_st, nb * 16 * 2, 2, ctx->fwd_luts_trivial, S(ctx));
+    launch_lut8(ctx->K, d_ggsw_f, ctx->d_kf_last, lut8, out8, d_st, nb * 16 * 2, 2, ctx->fwd_luts_trivial, ctx->d_masks_nonzero + 1, S(ctx));
     launch_ctr_finish(d_st, d_ct, d_out, nb, S(ctx));
     ctx->launches += 2;
     return check_launch("ctr last round");
@@ -510,6 +499,17 @@ int cbs_ctx_create(const cbs_keyset *ks, int device, cbs_ctx **out)
         return fail(rc);
     if ((rc = upload(ctx, d_tw, tw.data(), tw.size() * 8)) || (rc = upload(ctx, d_tw128, tw128.data(), tw128.size() * 8)))
         return fail(rc);
+    {
+        // device flags "some LUT mask word is non-zero" (k_masks_nonzero after every LUT upload); 1 = not trivial until known
+        void *d_flags = nullptr;
+        const int ones[2] = {1, 1};
+        if ((rc = key_alloc(ctx, sizeof(ones), &d_flags))) return fail(rc);
+        ctx->d_masks_nonzero = (int *)d_flags;
+        if (cudaMemcpy(d_flags, ones, sizeof(ones), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("cudaMemcpy(flags) failed");
+            return fail(CBS_ERR_CUDA);
+        }
+    }
     ctx->K.tw = (const double *)d_tw;
     ctx->K.tw128 = (const double *)d_tw128;
     // staging buffer for the standard-domain keys (largest = bsk)
@@ -824,7 +824,7 @@ int cbs_lut8_eval(cbs_ctx *ctx, const uint64_t *ggsw_bits, int nbytes, const uin
     TRY(upload(ctx, d_li, li.data(), sizeof(int) * njobs));
     TRY(upload(ctx, d_oi, oi.data(), sizeof(int) * njobs));
     launch_ggsw_to_fourier(ctx->K, d_ggsw, d_ggsw_f, nbits, ctx->stream);
-    launch_lut8(ctx->K, d_ggsw_f, d_luts, d_li, d_oi, d_out, njobs, apb, 0, ctx->stream);
+    launch_lut8(ctx->K, d_ggsw_f, d_luts, d_li, d_oi, d_out, njobs, apb, 0, nullptr, ctx->stream);
     ctx->launches += 2;
     TRY(check_launch("k_lut8"));
     return download(ctx, out, d_out, (size_t)njobs * 4 * kLweBig * 8);
@@ -876,8 +876,11 @@ int cbs_trans_key_upload(cbs_ctx *ctx, const uint64_t *k10_9, const uint64_t *k8
     TRY(upload(ctx, ctx->d_k10_9, k10_9, (size_t)CBS_K10_9_WORDS * 8));
     TRY(upload(ctx, ctx->d_k8_1, k8_1, (size_t)CBS_K8_1_WORDS * 8));
     TRY(upload(ctx, ctx->d_k0, k0, (size_t)CBS_K0_WORDS * 8));
-    // the host scan of the LUT masks (17 MB when they are all zero) runs while the 29 MB copy is in flight
-    ctx->inv_luts_trivial = all_masks_zero(k8_1, 8 * 4 * 16 * 2) && all_masks_zero(k0, 16 * 2);
+    // are the LUT accumulators trivial (zero masks)?  Answered on the device, right behind the copies
+    CUDA_TRY(cudaMemsetAsync(ctx->d_masks_nonzero, 0, sizeof(int), ctx->stream));
+    launch_masks_nonzero(ctx->d_k8_1, 8 * 4 * 16 * 2, ctx->d_masks_nonzero, ctx->stream);
+    launch_masks_nonzero(ctx->d_k0, 16 * 2, ctx->d_masks_nonzero, ctx->stream);
+    ctx->inv_luts_trivial = 0;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the caller owns the host buffers again
     ctx->have_trans_key = true;
     return CBS_OK;
@@ -911,6 +914,9 @@ int cbs_aes128_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const u
     CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_after, 0));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_k8_1, k8_1, (size_t)CBS_K8_1_WORDS * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_k0, k0, (size_t)CBS_K0_WORDS * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_masks_nonzero, 0, sizeof(int), ctx->copy_stream));
+    launch_masks_nonzero(ctx->d_k8_1, 8 * 4 * 16 * 2, ctx->d_masks_nonzero, ctx->copy_stream);
+    launch_masks_nonzero(ctx->d_k0, 16 * 2, ctx->d_masks_nonzero, ctx->copy_stream);
     CUDA_TRY(cudaEventRecord(ctx->ev_keys, ctx->copy_stream));
     TRY(upload(ctx, ctx->d_k10_9, k10_9, (size_t)CBS_K10_9_WORDS * 8));
     uint8_t *d_ct;
@@ -918,7 +924,7 @@ int cbs_aes128_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const u
     TRY(ws_typed(ctx, "io_ct", (size_t)nblocks * 16, &d_ct));
     TRY(ws_typed(ctx, "io_result", (size_t)nblocks * 128 * kLweBig, &d_out));
     TRY(upload(ctx, d_ct, ct, (size_t)nblocks * 16));
-    ctx->inv_luts_trivial = all_masks_zero(k8_1, 8 * 4 * 16 * 2) && all_masks_zero(k0, 16 * 2);  // host scan, copies in flight
+    ctx->inv_luts_trivial = 0;
     ctx->have_trans_key = true;
     ctx->keys_in_flight = true;
     int rc = dev_transcipher(ctx, d_ct, nblocks, d_out);
@@ -942,7 +948,10 @@ int cbs_fwd_trans_key_upload(cbs_ctx *ctx, const uint64_t *kf_first, const uint6
     TRY(upload(ctx, ctx->d_kf_first, kf_first, (size_t)CBS_KF_FIRST_WORDS * 8));
     TRY(upload(ctx, ctx->d_kf_mid, kf_mid, (size_t)CBS_KF_MID_WORDS * 8));
     TRY(upload(ctx, ctx->d_kf_last, kf_last, (size_t)CBS_KF_LAST_WORDS * 8));
-    ctx->fwd_luts_trivial = all_masks_zero(kf_mid, 8 * 3 * 16 * 2) && all_masks_zero(kf_last, 16 * 2);  // overlaps the copies
+    CUDA_TRY(cudaMemsetAsync(ctx->d_masks_nonzero + 1, 0, sizeof(int), ctx->stream));
+    launch_masks_nonzero(ctx->d_kf_mid, 8 * 3 * 16 * 2, ctx->d_masks_nonzero + 1, ctx->stream);
+    launch_masks_nonzero(ctx->d_kf_last, 16 * 2, ctx->d_masks_nonzero + 1, ctx->stream);
+    ctx->fwd_luts_trivial = 0;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->have_fwd_key = true;
     return CBS_OK;

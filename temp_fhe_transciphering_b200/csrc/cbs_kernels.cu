@@ -1804,9 +1804,12 @@ __global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8_v2(const double *__
                                                                  const int *__restrict__ lut_index,
                                                                  const int *__restrict__ out_index,
                                                                  uint64_t *__restrict__ out, int njobs, int accs_per_byte,
-                                                                 const double *__restrict__ twtab, int groups, int trivial)
+                                                                 const double *__restrict__ twtab, int groups, int trivial_arg,
+                                                                 const int *__restrict__ masks_nonzero)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // trivial accumulators: promised by the caller, or found by k_masks_nonzero right after the key upload (device flag)
+    const int trivial = trivial_arg || (masks_nonzero != nullptr && *masks_nonzero == 0);
     const int gi = threadIdx.x >> 6;
     const int job = (gi < groups) ? blockIdx.x * groups + gi : njobs;
     unsigned char *ring = smem_raw + (size_t)kLutGroups * kLut2GroupSmem;
@@ -1936,8 +1939,27 @@ __global__ void __launch_bounds__(64 * kLutGroups, 1) k_lut8_v2(const double *__
     }
 }
 
+// flag |= 1 if any mask word (first two polynomials) of the `count` GLWE accumulators at `luts` is non-zero.  Replaces a host
+// scan of up to 17 MB per key upload that sat on the critical path of every end-to-end call.
+__global__ void __launch_bounds__(256) k_masks_nonzero(const uint64_t *__restrict__ luts, int count, int *__restrict__ flag)
+{
+    uint64_t acc = 0;
+    for (int g = blockIdx.x; g < count; g += gridDim.x) {
+        const uint64_t *m = luts + (size_t)g * kGlweWords;
+        for (int j = threadIdx.x; j < 2048; j += 256) acc |= m[j];
+    }
+    if (__syncthreads_or(acc != 0) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+void launch_masks_nonzero(const uint64_t *luts, int count, int *flag, cudaStream_t s)
+{
+    if (count <= 0) return;
+    k_masks_nonzero<<<count < 592 ? count : 592, 256, 0, s>>>(luts, count, flag);
+}
+
 void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts, const int *lut_index,
-                 const int *out_index, uint64_t *out, int njobs, int accs_per_byte, int trivial, cudaStream_t s)
+                 const int *out_index, uint64_t *out, int njobs, int accs_per_byte, int trivial, const int *masks_nonzero,
+                 cudaStream_t s)
 {
     if (njobs <= 0) return;
     static bool attr_done[64] = {false};
@@ -1958,7 +1980,7 @@ void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts
     // njobs is a whole number of bytes for every caller (cbs_api.cu); a ragged tail would read another byte's selectors
     if (njobs % accs_per_byte != 0) return;
     k_lut8_v2<<<njobs / groups, 64 * kLutGroups, kLut2SmemBytes, s>>>(ggsw_f, luts, lut_index, out_index, out, njobs, accs_per_byte, K.tw,
-                                                                      groups, trivial);
+                                                                      groups, trivial, masks_nonzero);
 }
 
 // ------------------------------------------------------------------------------------------------

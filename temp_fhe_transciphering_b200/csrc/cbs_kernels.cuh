@@ -63,7 +63,10 @@ void launch_ggsw_to_fourier(const DeviceKeys &K, const uint64_t *ggsw_std, doubl
 //     lut[lut_index[j]] (GLWE), outputs 4 LWE(2048) written to out[out_index[j] + {0,1,2,3}].
 //     trivial = 1 promises that every accumulator is a trivial GLWE (zero mask polynomials).
 void launch_lut8(const DeviceKeys &K, const double *ggsw_f, const uint64_t *luts, const int *lut_index,
-                 const int *out_index, uint64_t *out, int njobs, int accs_per_byte, int trivial, cudaStream_t s);
+                 const int *out_index, uint64_t *out, int njobs, int accs_per_byte, int trivial, const int *masks_nonzero,
+                 cudaStream_t s);
+// *flag |= 1 if any mask word of the `count` GLWE accumulators at `luts` is non-zero (device-side "are these LUTs trivial?")
+void launch_masks_nonzero(const uint64_t *luts, int count, int *flag, cudaStream_t s);
 
 // a7 with gathered selectors (inner-product circuit): job j runs the ladder over the GGSWs ggsw_f[sel[j*8 + i]]
 //     (i = 0..7, -1 = constant-0 selector) on accumulator luts[lut_index[j]], 4 LWE(2048) out at out[out_index[j] + q]
