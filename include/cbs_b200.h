@@ -175,7 +175,8 @@ int cbs_aes_inv_linear(cbs_ctx *ctx, const uint64_t *t4, int nblocks, uint64_t *
 
 /* aes_to_lwe_trasnciphering, src/bin/server_encrypted_aes_decryption.rs:28-191, for nblocks
  * independent 16-byte ECB blocks.  out[nblocks][128] big LWE, MSB-first inside each byte
- * (the exact payload of ciphertext_aes_download/result.bin). */
+ * (the exact payload of ciphertext_aes_download/result.bin).  Synchronous for the caller (all host buffers are free again
+ * on return); inside, the round 8..0 LUTs travel on a copy stream while the first rounds and the first blind rotation run. */
 int cbs_aes128_transcipher(cbs_ctx *ctx, const uint8_t *ct, int nblocks, const uint64_t *k10_9, const uint64_t *k8_1,
                            const uint64_t *k0, uint64_t *out);
 /* CTR-mode transciphering (forward AES on the public counter blocks IV+i, 128-bit big-endian counter as
