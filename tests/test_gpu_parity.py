@@ -372,3 +372,33 @@ def test_golden_pin_b_on_gpu(cbs):
     assert abs(np.log2(np.sqrt(np.mean(ref_err ** 2))) - ref["noise_log2_std"]) < 0.01
     err = ref_io.bit_error(ref_io.lwe_phase(got, ks.glwe_sk), bits).astype(np.float64)
     assert np.abs(err).max() < 2.0 * np.abs(ref_err).max()
+
+
+def test_aes_transcipher_with_non_trivial_luts(ctx, keyset, aes_key, trans_key):
+    """The reference always writes the round 8..0 LUTs as trivial GLWE (zero masks, data_struct.rs:145-151) and the ladder
+    skips the mask transforms of its first CMux when the device-side check (k_masks_nonzero) says so.  Here one accumulator
+    gets a real mask: a GLWE encryption of zero (difference of two encryptions of the same table) is added to it, which
+    leaves every decryption unchanged - provided the check notices and the full first CMux runs."""
+    import aes_clear
+    import ref_io
+    k10_9, k8_1, k0 = trans_key
+    other = keyset.gen_transciphering_keys(aes_key, 424242)[0]
+    if (other == k10_9).all():  # same seed as the fixture: take another one
+        other = keyset.gen_transciphering_keys(aes_key, 424243)[0]
+    zero = (k10_9[0, 0, 0].astype(np.uint64) - other[0, 0, 0].astype(np.uint64))
+    assert zero[:2048].any()
+    k8_1 = k8_1.copy()
+    with np.errstate(over="ignore"):
+        for r in range(8):
+            k8_1[r, 0, 0, 0] = k8_1[r, 0, 0, 0] + zero
+    assert k8_1[0, 0, 0, 0, :2048].any()
+    pt = bytes(np.random.default_rng(11).integers(0, 256, 16, dtype=np.uint8))
+    ct = aes_clear.ecb_encrypt(aes_key, pt)
+    got = ctx.aes_to_lwe_transciphering(ct, k10_9, k8_1, k0)
+    bits, std, mx = ref_io.noise_stats(got.reshape(-1, 2049), keyset.glwe_sk)
+    assert np.packbits(bits).tobytes() == pt
+    assert std < 58.6 and mx < 61.2, (std, mx)
+    # and back to the trivial LUTs of the fixture (later tests share the context)
+    got = ctx.aes_to_lwe_transciphering(ct, *trans_key)
+    bits, _, _ = ref_io.noise_stats(got.reshape(-1, 2049), keyset.glwe_sk)
+    assert np.packbits(bits).tobytes() == pt
